@@ -1,0 +1,664 @@
+// K3 / K4a: per-tile front-to-back alpha compositing with per-pixel SH colour, forward and
+// backward.  Replaces tile_based_vol_rendering_sh_entry / ..._backward_sh_entry
+// (vol_render_sh.h:97-248, 268-455) and their _with_bg variants (vol_render_bg.h).
+//
+// One CTA (256 threads = 16x16 pixels, warps own 8x4 pixel blocks) per tile.  Gaussians of the
+// tile's list are staged in batches into shared memory with cp.async (LDGSTS), double-buffered:
+// a 48-byte staging record per Gaussian (3 x 16 B) plus its 3*C*C SH coefficients, gathered by id.
+// Per (pixel, Gaussian) pair the fast path costs ~10 FP32 instructions: a pre-scaled conic form
+// gives log2(G) and the 1/255 skip test is a compare against a per-Gaussian threshold, so no
+// exponential is evaluated for skipped pairs.  Decisions that fall within a small margin of the
+// threshold are re-evaluated in the reference's exact FP32 operation order (kernels.h:172-193 as
+// compiled: FMA contraction pattern taken from the reference's SASS) so that skip decisions --
+// which move a pixel by up to 1/255 -- match the reference bit for bit.
+// Warp-ballot early termination: a warp stops evaluating when all its pixels have T < thresh, the
+// CTA stops staging when all warps are done.
+//
+// Backward: forward recompute in list order (the reference's own scheme, `final - prefix` suffix).
+// Per contributing (warp, Gaussian) the 3*C*C + 6 partial sums over the warp's 32 pixels are
+// reduced through a shared-memory transpose (w[c][pixel] x Y[pixel][k] as a tiny GEMV per lane)
+// into warp-private accumulators, summed over the 8 warps per batch and flushed with one vector
+// red.global.add.v4.f32 per 4 coefficients: ~14 global reductions per (tile, Gaussian) instead of
+// the reference's 55 shared atomics per (pixel, Gaussian) + 55 global atomics per (tile, Gaussian).
+#include "common.cuh"
+
+namespace gs3d {
+
+constexpr int TILE = 16;
+constexpr int NTHREADS = 256;
+constexpr int NWARPS = 8;
+constexpr float MIN_RENDER_ALPHA = 1 / 255.0f;  // common.h:90
+constexpr float DECISION_MARGIN = 0.004f;       // log2 units around the skip threshold
+
+struct CompositeParams {
+  const float4 *records;
+  const float *sh;
+  uint32_t sh_sg, sh_sc;
+  const int32_t *start, *end, *ids;
+  float *out;
+  const float *topleft, *c2w;
+  uint32_t ntw, nth;
+  float psx, psy;
+  uint32_t H, W;
+  float thresh;
+  const float *bg;
+  float *final_T;
+  int32_t *n_contrib;
+  int exact;
+  // backward only
+  const float *out_saved, *grad_out;
+  float *g_mean, *g_cov, *g_sh, *g_alpha;
+  uint32_t gsh_sg, gsh_sc;
+  int sh_vec;   // SH rows are 16-byte addressable (staging)
+  int gsh_vec;  // grad SH rows are 16-byte addressable (vector reductions)
+};
+
+// ---------------------------------------------------------------- small device helpers
+
+__device__ __forceinline__ void cp_async_16(void *smem, const void *gmem) {
+  uint32_t s = (uint32_t)__cvta_generic_to_shared(smem);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(s), "l"(gmem));
+}
+__device__ __forceinline__ void cp_async_4(void *smem, const void *gmem) {
+  uint32_t s = (uint32_t)__cvta_generic_to_shared(smem);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"(s), "l"(gmem));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;\n" ::"n"(N));
+}
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ void red_add_v4(float *addr, float4 v) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};\n" ::"l"(addr), "f"(v.x), "f"(v.y),
+               "f"(v.z), "f"(v.w)
+               : "memory");
+}
+__device__ __forceinline__ float fast_sigmoid(float s) {
+  return __fdividef(1.0f, 1.0f + __expf(-s));
+}
+
+// shencoder.h:13-55, per-pixel basis (quirk Q2)
+template <int C>
+__device__ __forceinline__ void sh_basis(float x, float y, float z, float *o) {
+  o[0] = 0.28209479177387814f;
+  if constexpr (C > 1) {
+    o[1] = -0.48860251190291987f * y;
+    o[2] = 0.48860251190291987f * z;
+    o[3] = -0.48860251190291987f * x;
+  }
+  if constexpr (C > 2) {
+    float xy = x * y, xz = x * z, yz = y * z, x2 = x * x, y2 = y * y, z2 = z * z;
+    o[4] = 1.0925484305920792f * xy;
+    o[5] = -1.0925484305920792f * yz;
+    o[6] = 0.94617469575755997f * z2 - 0.31539156525251999f;
+    o[7] = -1.0925484305920792f * xz;
+    o[8] = 0.54627421529603959f * x2 - 0.54627421529603959f * y2;
+    if constexpr (C > 3) {
+      o[9] = 0.59004358992664352f * y * (-3.0f * x2 + y2);
+      o[10] = 2.8906114426405538f * xy * z;
+      o[11] = 0.45704579946446572f * y * (1.0f - 5.0f * z2);
+      o[12] = 0.3731763325901154f * z * (5.0f * z2 - 3.0f);
+      o[13] = 0.45704579946446572f * x * (1.0f - 5.0f * z2);
+      o[14] = 1.4453057213202769f * z * (x2 - y2);
+      o[15] = 0.59004358992664352f * x * (-x2 + 3.0f * y2);
+    }
+  }
+}
+
+// vol_render_sh.h:48-65 + :213-217: direction from the first nine floats of the [3,4] c2w (Q1).
+template <int C>
+__device__ __forceinline__ void pixel_basis(const float *c2w, float px, float py, float *Y) {
+  float d0 = c2w[0] * px + c2w[1] * py + c2w[2] * 1.0f;
+  float d1 = c2w[3] * px + c2w[4] * py + c2w[5] * 1.0f;
+  float d2 = c2w[6] * px + c2w[7] * py + c2w[8] * 1.0f;
+  float len = sqrtf(d0 * d0 + d1 * d1 + d2 * d2);
+  sh_basis<C>(d0 / len, d1 / len, d2 / len, Y);
+}
+
+// The reference's Gaussian in its compiled operation order (kernels.h:172-193; SASS of
+// tile_based_vol_rendering_sh_entry<4>, sm_100a, nvcc 12.9):
+//   det  = fma(c0, c3, -(c2*c1));  tmpy = fma(c0, y, -(x*c1));  tmpx = fma(x, c3, -(c2*y));
+//   num  = fma(x, tmpx, y*tmpy);   radial = num / det (IEEE);  arg = radial >= 0 ? -0.5*radial : -500
+__device__ __forceinline__ float gaussian_exact(float x, float y, float4 cv) {
+  float det = __fmaf_rn(cv.x, cv.w, -__fmul_rn(cv.z, cv.y));
+  float tmpy = __fmaf_rn(cv.x, y, -__fmul_rn(x, cv.y));
+  float tmpx = __fmaf_rn(x, cv.w, -__fmul_rn(cv.z, y));
+  float num = __fmaf_rn(x, tmpx, __fmul_rn(y, tmpy));
+  float radial = __fdiv_rn(num, det);
+  float arg = (radial < 0.0f) ? -500.0f : __fmul_rn(radial, -0.5f);
+  return expf(arg);
+}
+
+// Returns true when the pair contributes (alpha_*G >= 1/255); G is valid only then.
+__device__ __forceinline__ bool eval_pair(float px, float py, const float4 r0, const float4 r1,
+                                          const float4 *r2p, int exact, float &G) {
+  float dx = px - r0.x, dy = py - r0.y;
+  float pw = (r1.x * dx) * dx + ((r1.y * dx) * dy + (r1.z * dy) * dy);  // log2 G
+  float diff = pw - r0.w;
+  if (exact && (fabsf(diff) < DECISION_MARGIN || pw > -1e-5f)) {
+    float val = gaussian_exact(dx, dy, *r2p);
+    G = val;
+    return !(r0.z * val < MIN_RENDER_ALPHA);
+  }
+  if (!(diff >= 0.0f) || pw > 0.0f) return false;
+  G = ex2_approx(pw);
+  return true;
+}
+
+// Stage `nb` Gaussians (ids already in s_ids) into shared memory with cp.async.
+template <int CC, int B>
+__device__ __forceinline__ void stage_batch(const CompositeParams &p, const int *s_ids, int nb,
+                                            float4 *s_rec, float *s_sh) {
+  constexpr int SHF = 3 * CC;
+  for (int e = threadIdx.x; e < nb * 3; e += NTHREADS) {
+    int j = e / 3, r = e - 3 * j;
+    cp_async_16(s_rec + e, p.records + 3 * (size_t)s_ids[j] + r);
+  }
+  if (p.sh_vec) {
+    constexpr int V = SHF / 4 > 0 ? SHF / 4 : 1;
+    for (int e = threadIdx.x; e < nb * V; e += NTHREADS) {
+      int j = e / V, r = (e - V * j) * 4;
+      int c = r / CC, k = r - c * CC;
+      cp_async_16(s_sh + j * SHF + r, p.sh + (size_t)s_ids[j] * p.sh_sg + c * p.sh_sc + k);
+    }
+  } else {
+    for (int e = threadIdx.x; e < nb * SHF; e += NTHREADS) {
+      int j = e / SHF, r = e - SHF * j;
+      int c = r / CC, k = r - c * CC;
+      cp_async_4(s_sh + e, p.sh + (size_t)s_ids[j] * p.sh_sg + c * p.sh_sc + k);
+    }
+  }
+}
+
+template <int CC>
+__device__ __forceinline__ void sh_colour(const float *h, const float *Y, float coeff, float *y) {
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    float s = 0.0f;
+    if constexpr (CC % 4 == 0) {
+      const float4 *h4 = reinterpret_cast<const float4 *>(h + c * CC);
+#pragma unroll
+      for (int k = 0; k < CC / 4; ++k) {
+        float4 v = h4[k];
+        s = fmaf(v.x, Y[4 * k], s);
+        s = fmaf(v.y, Y[4 * k + 1], s);
+        s = fmaf(v.z, Y[4 * k + 2], s);
+        s = fmaf(v.w, Y[4 * k + 3], s);
+      }
+    } else {
+#pragma unroll
+      for (int k = 0; k < CC; ++k) s = fmaf(h[c * CC + k], Y[k], s);
+    }
+    float v = fast_sigmoid(s);
+    if (isnan(v * coeff)) v = 0.0f;  // vol_render_sh.h:151-159
+    y[c] = v;
+  }
+}
+
+// ---------------------------------------------------------------- forward
+
+template <int C, int B>
+__global__ void __launch_bounds__(NTHREADS)
+composite_fwd_kernel(const CompositeParams p) {
+  constexpr int CC = C * C;
+  constexpr int SHF = 3 * CC;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  float4 *s_rec = reinterpret_cast<float4 *>(smem_raw);        // [2][B][3]
+  float *s_sh = reinterpret_cast<float *>(s_rec + 2 * B * 3);  // [2][B][SHF]
+  int *s_ids = reinterpret_cast<int *>(s_sh + 2 * B * SHF);    // [2][B]
+
+  const int tile_id = blockIdx.x;
+  const int tile_y = tile_id / p.ntw, tile_x = tile_id - tile_y * p.ntw;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int lx = 8 * (warp & 1) + (lane & 7), ly = 4 * (warp >> 1) + (lane >> 3);
+  const uint32_t gx = tile_x * TILE + lx, gy = tile_y * TILE + ly;
+  const bool inside = gx < p.W && gy < p.H;
+  const size_t pix = (size_t)gy * p.W + gx;
+
+  const int first = p.start[tile_id];
+  const int n_this = first == -1 ? 0 : p.end[tile_id] - first;
+  if (first == -1) {  // vol_render_sh.h:185-188 / vol_render_bg.h:28-37
+    if (inside) {
+      if (p.bg) {
+        p.out[3 * pix + 0] = p.bg[0];
+        p.out[3 * pix + 1] = p.bg[1];
+        p.out[3 * pix + 2] = p.bg[2];
+      }
+      if (p.final_T) p.final_T[pix] = 1.0f;
+      if (p.n_contrib) p.n_contrib[pix] = 0;
+    }
+    return;
+  }
+  if (n_this <= 0) return;
+
+  // pixel corner in camera-plane units (quirk Q4), same expression as vol_render_sh.h:213-214
+  const float px = p.topleft[0] + gx * p.psx, py = p.topleft[1] + gy * p.psy;
+  float Y[CC];
+  pixel_basis<C>(p.c2w, px, py, Y);
+
+  float T = 1.0f, o0 = 0.0f, o1 = 0.0f, o2 = 0.0f;
+  int last = 0;
+  bool alive = inside;  // T starts at 1 >= thresh for any sane thresh; test is applied per Gaussian
+  const int32_t *ids = p.ids + first;
+  const int n_batches = (n_this + B - 1) / B;
+  const int exact = p.exact;
+
+  int my_id = (threadIdx.x < B && threadIdx.x < n_this) ? ids[threadIdx.x] : 0;
+  for (int b = 0; b <= n_batches; ++b) {
+    if (b < n_batches) {
+      const int buf = b & 1;
+      const int nb = min(B, n_this - b * B);
+      if (threadIdx.x < B) s_ids[buf * B + threadIdx.x] = my_id;
+      __syncthreads();
+      int nxt = (b + 1) * B + threadIdx.x;
+      my_id = (threadIdx.x < B && nxt < n_this) ? ids[nxt] : 0;
+      stage_batch<CC, B>(p, s_ids + buf * B, nb, s_rec + buf * B * 3, s_sh + buf * B * SHF);
+    }
+    cp_async_commit();
+    if (b == 0) continue;
+    cp_async_wait<1>();
+    __syncthreads();
+    {
+      const int cb = b - 1;
+      const int buf = cb & 1;
+      const int nb = min(B, n_this - cb * B);
+      const float4 *rec = s_rec + buf * B * 3;
+      const float *shb = s_sh + buf * B * SHF;
+      for (int j = 0; j < nb; ++j) {
+        if (!__any_sync(0xffffffffu, alive)) break;
+        if (alive) {
+          if (T < p.thresh) {  // vol_render_sh.h:121-123, tested before each Gaussian
+            alive = false;
+          } else {
+            const float4 r0 = rec[3 * j], r1 = rec[3 * j + 1];
+            float G;
+            if (eval_pair(px, py, r0, r1, rec + 3 * j + 2, exact, G)) {
+              const float a = r0.z;
+              float coeff = (a * T) * G;
+              if (isnan(coeff)) coeff = 0.0f;
+              float y[3];
+              sh_colour<CC>(shb + j * SHF, Y, coeff, y);
+              o0 += coeff * y[0];
+              o1 += coeff * y[1];
+              o2 += coeff * y[2];
+              T *= (1 - a * G);
+              last = cb * B + j + 1;
+            }
+          }
+        }
+      }
+    }
+    // all pixels of the tile finished -> stop staging (uniform decision, doubles as barrier)
+    if (__syncthreads_and(!alive || T < p.thresh)) break;
+  }
+  cp_async_wait<0>();
+  if (!inside) return;
+  if (p.bg && T > p.thresh) {  // vol_render_bg.h:90-94
+    o0 = o0 * T + p.bg[0] * (1.0f - T);
+    o1 = o1 * T + p.bg[1] * (1.0f - T);
+    o2 = o2 * T + p.bg[2] * (1.0f - T);
+  }
+  p.out[3 * pix + 0] = o0;
+  p.out[3 * pix + 1] = o1;
+  p.out[3 * pix + 2] = o2;
+  if (p.final_T) p.final_T[pix] = T;
+  if (p.n_contrib) p.n_contrib[pix] = last;
+}
+
+// ---------------------------------------------------------------- backward
+
+template <int C, int B>
+__global__ void __launch_bounds__(NTHREADS)
+composite_bwd_kernel(const CompositeParams p) {
+  constexpr int CC = C * C;
+  constexpr int SHF = 3 * CC;
+  constexpr int ROW = SHF + 6;            // 3*CC SH sums, then gmx gmy g00 g01 g11 galpha
+  constexpr int ROWP = (ROW + 3) & ~3;    // padded to float4
+  constexpr int NQ = ROWP / 4;
+  constexpr int KL = CC < 16 ? CC : 16;   // lanes per half that own an SH column
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  float4 *s_rec = reinterpret_cast<float4 *>(smem_raw);           // [2][B][3]
+  float *s_sh = reinterpret_cast<float *>(s_rec + 2 * B * 3);     // [2][B][SHF]
+  float *s_w = s_sh + 2 * B * SHF;                                // [NWARPS][9][32]
+  float *s_acc = s_w + NWARPS * 9 * 32;                           // [NWARPS][B][ROWP]
+  int *s_ids = reinterpret_cast<int *>(s_acc + NWARPS * B * ROWP);  // [2][B]
+
+  const int tile_id = blockIdx.x;
+  const int tile_y = tile_id / p.ntw, tile_x = tile_id - tile_y * p.ntw;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int lx = 8 * (warp & 1) + (lane & 7), ly = 4 * (warp >> 1) + (lane >> 3);
+  const uint32_t gx = tile_x * TILE + lx, gy = tile_y * TILE + ly;
+  const bool inside = gx < p.W && gy < p.H;
+  const size_t pix = (size_t)gy * p.W + gx;
+
+  const int first = p.start[tile_id];
+  if (first == -1) return;
+  const int n_this = p.end[tile_id] - first;
+  if (n_this <= 0) return;
+
+  const float px = p.topleft[0] + gx * p.psx, py = p.topleft[1] + gy * p.psy;
+  float Y[CC];
+  pixel_basis<C>(p.c2w, px, py, Y);
+
+  // Yt[i] = Y_k(pixel 16*half + i) for this lane's (k = lane & 15, half = lane >> 4):
+  // transposed through the (not yet used) accumulator area.
+  const int kcol = lane & 15, half = lane >> 4;
+  float Yt[16];
+  {
+    constexpr int TS = CC + 1;            // [32][CC+1] per warp; 32*(CC+1) <= B*ROWP for B >= 32
+    float *tr = s_acc + warp * 32 * TS;
+#pragma unroll
+    for (int k = 0; k < CC; ++k) tr[lane * TS + k] = inside ? Y[k] : 0.0f;
+    __syncwarp();
+#pragma unroll
+    for (int i = 0; i < 16; ++i) Yt[i] = (kcol < CC) ? tr[(16 * half + i) * TS + kcol] : 0.0f;
+  }
+  __syncthreads();
+  for (int e = threadIdx.x; e < NWARPS * B * ROWP; e += NTHREADS) s_acc[e] = 0.0f;
+
+  float g0 = 0.f, g1 = 0.f, g2 = 0.f, f0 = 0.f, f1 = 0.f, f2 = 0.f;
+  if (inside) {
+    g0 = p.grad_out[3 * pix + 0]; g1 = p.grad_out[3 * pix + 1]; g2 = p.grad_out[3 * pix + 2];
+    f0 = p.out_saved[3 * pix + 0]; f1 = p.out_saved[3 * pix + 1]; f2 = p.out_saved[3 * pix + 2];
+  }
+  float T = 1.0f, o0 = 0.0f, o1 = 0.0f, o2 = 0.0f;
+  bool alive = inside;
+  const int32_t *ids = p.ids + first;
+  const int n_batches = (n_this + B - 1) / B;
+  const int exact = p.exact;
+  float *w_me = s_w + warp * 9 * 32;
+  float *acc_me = s_acc + warp * B * ROWP;
+  constexpr float INV_K = 1.0f / (-0.5f * 1.4426950408889634f);  // undo the conic pre-scale
+
+  int my_id = (threadIdx.x < B && threadIdx.x < n_this) ? ids[threadIdx.x] : 0;
+  for (int b = 0; b <= n_batches; ++b) {
+    if (b < n_batches) {
+      const int buf = b & 1;
+      const int nb = min(B, n_this - b * B);
+      if (threadIdx.x < B) s_ids[buf * B + threadIdx.x] = my_id;
+      __syncthreads();  // ids visible; previous flush (acc zeroing) complete
+      int nxt = (b + 1) * B + threadIdx.x;
+      my_id = (threadIdx.x < B && nxt < n_this) ? ids[nxt] : 0;
+      stage_batch<CC, B>(p, s_ids + buf * B, nb, s_rec + buf * B * 3, s_sh + buf * B * SHF);
+    }
+    cp_async_commit();
+    if (b == 0) continue;
+    cp_async_wait<1>();
+    __syncthreads();
+    const int cb = b - 1;
+    const int buf = cb & 1;
+    const int nb = min(B, n_this - cb * B);
+    {
+      const float4 *rec = s_rec + buf * B * 3;
+      const float *shb = s_sh + buf * B * SHF;
+      for (int j = 0; j < nb; ++j) {
+        if (!__any_sync(0xffffffffu, alive)) break;
+        float w0 = 0.f, w1 = 0.f, w2 = 0.f, gmx = 0.f, gmy = 0.f, g00 = 0.f, g01 = 0.f, g11 = 0.f,
+              ga = 0.f;
+        bool contrib = false;
+        if (alive) {
+          if (T < p.thresh) {
+            alive = false;
+          } else {
+            const float4 r0 = rec[3 * j], r1 = rec[3 * j + 1];
+            float G;
+            if (eval_pair(px, py, r0, r1, rec + 3 * j + 2, exact, G)) {
+              contrib = true;
+              const float a = r0.z;
+              const float aG = a * G;
+              float coeff = (a * T) * G;
+              if (isnan(coeff)) coeff = 0.0f;
+              float y[3];
+              sh_colour<CC>(shb + j * SHF, Y, coeff, y);
+              o0 += coeff * y[0];
+              o1 += coeff * y[1];
+              o2 += coeff * y[2];
+              // vol_render_sh.h:328-333
+              w0 = coeff * (y[0] * (1.0f - y[0])) * g0;
+              w1 = coeff * (y[1] * (1.0f - y[1])) * g1;
+              w2 = coeff * (y[2] * (1.0f - y[2])) * g2;
+              // vol_render_sh.h:336-342
+              const float inv1m = 1.0f / (1.0f - aG);
+              float P = g0 * (y[0] * T - (f0 - o0) * inv1m);
+              P += g1 * (y[1] * T - (f1 - o1) * inv1m);
+              P += g2 * (y[2] * T - (f2 - o2) * inv1m);
+              // kernels.h:394-418 with the inverse covariance recovered from the conic
+              const float dx = px - r0.x, dy = py - r0.y;
+              const float i00 = r1.x * INV_K, i11 = r1.z * INV_K, i01 = -0.5f * r1.y * INV_K;
+              const float vx = dx * i00 - dy * i01, vy = dy * i11 - dx * i01;
+              const float gam = P * aG;
+              gmx = gam * vx;
+              gmy = gam * vy;
+              g00 = 0.5f * gam * vx * vx;
+              g01 = 0.5f * gam * vx * vy;
+              g11 = 0.5f * gam * vy * vy;
+              ga = P * G;
+              T *= (1 - aG);
+            }
+          }
+        }
+        if (!__any_sync(0xffffffffu, contrib)) continue;
+        // ---- warp reduction over the 32 pixels through shared memory
+        w_me[0 * 32 + lane] = w0;
+        w_me[1 * 32 + lane] = w1;
+        w_me[2 * 32 + lane] = w2;
+        w_me[3 * 32 + lane] = gmx;
+        w_me[4 * 32 + lane] = gmy;
+        w_me[5 * 32 + lane] = g00;
+        w_me[6 * 32 + lane] = g01;
+        w_me[7 * 32 + lane] = g11;
+        w_me[8 * 32 + lane] = ga;
+        __syncwarp();
+        float a0 = 0.f, a1 = 0.f, a2 = 0.f;
+        {
+          const float4 *wa = reinterpret_cast<const float4 *>(w_me + 0 * 32 + 16 * half);
+          const float4 *wb = reinterpret_cast<const float4 *>(w_me + 1 * 32 + 16 * half);
+          const float4 *wc = reinterpret_cast<const float4 *>(w_me + 2 * 32 + 16 * half);
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            float4 va = wa[q], vb = wb[q], vc = wc[q];
+            a0 = fmaf(va.x, Yt[4 * q], a0); a0 = fmaf(va.y, Yt[4 * q + 1], a0);
+            a0 = fmaf(va.z, Yt[4 * q + 2], a0); a0 = fmaf(va.w, Yt[4 * q + 3], a0);
+            a1 = fmaf(vb.x, Yt[4 * q], a1); a1 = fmaf(vb.y, Yt[4 * q + 1], a1);
+            a1 = fmaf(vb.z, Yt[4 * q + 2], a1); a1 = fmaf(vb.w, Yt[4 * q + 3], a1);
+            a2 = fmaf(vc.x, Yt[4 * q], a2); a2 = fmaf(vc.y, Yt[4 * q + 1], a2);
+            a2 = fmaf(vc.z, Yt[4 * q + 2], a2); a2 = fmaf(vc.w, Yt[4 * q + 3], a2);
+          }
+        }
+        // six scalar sums: lane = 4*v + qd sums pixels 8*qd .. 8*qd+7 of row 3+v
+        float sv = 0.f;
+        {
+          const int v = lane >> 2, qd = lane & 3;
+          if (v < 6) {
+            const float4 *wr = reinterpret_cast<const float4 *>(w_me + (3 + v) * 32 + 8 * qd);
+            float4 x0 = wr[0], x1 = wr[1];
+            sv = ((x0.x + x0.y) + (x0.z + x0.w)) + ((x1.x + x1.y) + (x1.z + x1.w));
+          }
+        }
+        __syncwarp();
+        a0 += __shfl_xor_sync(0xffffffffu, a0, 16);
+        a1 += __shfl_xor_sync(0xffffffffu, a1, 16);
+        a2 += __shfl_xor_sync(0xffffffffu, a2, 16);
+        sv += __shfl_xor_sync(0xffffffffu, sv, 1);
+        sv += __shfl_xor_sync(0xffffffffu, sv, 2);
+        float *row = acc_me + j * ROWP;
+        if (lane < KL) {
+          row[0 * CC + lane] += a0;
+          row[1 * CC + lane] += a1;
+          row[2 * CC + lane] += a2;
+        }
+        if ((lane & 3) == 0 && lane < 24) row[SHF + (lane >> 2)] += sv;
+      }
+    }
+    __syncthreads();
+    // ---- flush: sum the 8 warp-private rows, reduce into global memory, re-zero
+    for (int e = threadIdx.x; e < nb * NQ; e += NTHREADS) {
+      const int j = e / NQ, q = e - NQ * j;
+      float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+      for (int w = 0; w < NWARPS; ++w) {
+        float4 *a4 = reinterpret_cast<float4 *>(s_acc + (w * B + j) * ROWP) + q;
+        float4 v = *a4;
+        s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+        *a4 = make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+      if (s.x == 0.f && s.y == 0.f && s.z == 0.f && s.w == 0.f) continue;
+      const size_t g = (size_t)s_ids[buf * B + j];
+      const float sv[4] = {s.x, s.y, s.z, s.w};
+      const int r0 = 4 * q;
+      if (CC % 4 == 0 && p.gsh_vec && r0 + 3 < SHF) {
+        const int c = r0 / CC, k = r0 - c * CC;
+        red_add_v4(p.g_sh + g * p.gsh_sg + c * p.gsh_sc + k, s);
+      } else {
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int r = r0 + u;
+          const float val = sv[u];
+          if (val == 0.f) continue;
+          if (r < SHF) {
+            const int c = r / CC, k = r - c * CC;
+            atomicAdd(p.g_sh + g * p.gsh_sg + c * p.gsh_sc + k, val);
+          } else {
+            const int v = r - SHF;
+            if (v == 0) atomicAdd(p.g_mean + 2 * g, val);
+            else if (v == 1) atomicAdd(p.g_mean + 2 * g + 1, val);
+            else if (v == 2) atomicAdd(p.g_cov + 4 * g, val);
+            else if (v == 3) { atomicAdd(p.g_cov + 4 * g + 1, val); atomicAdd(p.g_cov + 4 * g + 2, val); }
+            else if (v == 4) atomicAdd(p.g_cov + 4 * g + 3, val);
+            else if (v == 5) atomicAdd(p.g_alpha + g, val);
+          }
+        }
+      }
+    }
+    if (__syncthreads_and(!alive || T < p.thresh)) break;
+  }
+  cp_async_wait<0>();
+}
+
+// ---------------------------------------------------------------- host side
+
+template <int C, int B>
+static size_t fwd_smem() {
+  return (size_t)2 * B * 3 * sizeof(float4) + (size_t)2 * B * 3 * C * C * sizeof(float) +
+         (size_t)2 * B * sizeof(int);
+}
+template <int C, int B>
+static size_t bwd_smem() {
+  constexpr int ROWP = (3 * C * C + 6 + 3) & ~3;
+  return (size_t)2 * B * 3 * sizeof(float4) + (size_t)2 * B * 3 * C * C * sizeof(float) +
+         (size_t)NWARPS * 9 * 32 * sizeof(float) + (size_t)NWARPS * B * ROWP * sizeof(float) +
+         (size_t)2 * B * sizeof(int);
+}
+
+constexpr int FWD_B = 64;
+constexpr int BWD_B = 32;
+
+template <int C>
+static int launch_fwd(const CompositeParams &p, uint32_t n_tiles, cudaStream_t st) {
+  size_t sm = fwd_smem<C, FWD_B>();
+  GS3D_CUDA(cudaFuncSetAttribute(composite_fwd_kernel<C, FWD_B>,
+                                 cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+  composite_fwd_kernel<C, FWD_B><<<n_tiles, NTHREADS, sm, st>>>(p);
+  GS3D_LAUNCH_CHECK();
+  return GS3D_OK;
+}
+template <int C>
+static int launch_bwd(const CompositeParams &p, uint32_t n_tiles, cudaStream_t st) {
+  size_t sm = bwd_smem<C, BWD_B>();
+  GS3D_CUDA(cudaFuncSetAttribute(composite_bwd_kernel<C, BWD_B>,
+                                 cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+  composite_bwd_kernel<C, BWD_B><<<n_tiles, NTHREADS, sm, st>>>(p);
+  GS3D_LAUNCH_CHECK();
+  return GS3D_OK;
+}
+
+static bool aligned16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
+}  // namespace gs3d
+
+using namespace gs3d;
+
+extern "C" {
+
+int gs3d_composite_sh_forward(uint32_t M, const float *records, const float *sh_coeffs,
+                              uint32_t sh_stride_g, uint32_t sh_stride_c, const int32_t *start,
+                              const int32_t *end, const int32_t *gaussian_ids, float *out,
+                              const float *topleft, const float *c2w, uint32_t tile_size,
+                              uint32_t n_tiles_h, uint32_t n_tiles_w, float pixel_size_x,
+                              float pixel_size_y, uint32_t H, uint32_t W, uint32_t C, float thresh,
+                              const float *bg_rgb, float *final_T, int32_t *n_contrib,
+                              int exact_decisions, void *stream) {
+  (void)M;
+  GS3D_REQUIRE(tile_size == TILE, GS3D_EUNSUPPORTED,
+               "compositing kernels support tile_size 16 only (got %u)", tile_size);
+  GS3D_REQUIRE(C >= 1 && C <= 4, GS3D_EINVAL, "SH order C must be 1..4 (got %u)", C);
+  const uint32_t n_tiles = n_tiles_h * n_tiles_w;
+  if (n_tiles == 0 || H == 0 || W == 0) return GS3D_OK;
+  GS3D_REQUIRE(start && end && out && topleft && c2w, GS3D_EINVAL, "composite_sh_forward: null argument");
+  GS3D_REQUIRE(aligned16(records), GS3D_EINVAL, "records must be 16-byte aligned");
+  CompositeParams p = {};
+  p.records = reinterpret_cast<const float4 *>(records);
+  p.sh = sh_coeffs; p.sh_sg = sh_stride_g; p.sh_sc = sh_stride_c;
+  p.start = start; p.end = end; p.ids = gaussian_ids;
+  p.out = out; p.topleft = topleft; p.c2w = c2w;
+  p.ntw = n_tiles_w; p.nth = n_tiles_h; p.psx = pixel_size_x; p.psy = pixel_size_y;
+  p.H = H; p.W = W; p.thresh = thresh; p.bg = bg_rgb; p.final_T = final_T; p.n_contrib = n_contrib;
+  p.exact = exact_decisions;
+  const uint32_t CC = C * C;
+  p.sh_vec = (CC % 4 == 0) && (sh_stride_g % 4 == 0) && (sh_stride_c % 4 == 0) && aligned16(sh_coeffs);
+  cudaStream_t st = as_stream(stream);
+  switch (C) {
+    case 1: return launch_fwd<1>(p, n_tiles, st);
+    case 2: return launch_fwd<2>(p, n_tiles, st);
+    case 3: return launch_fwd<3>(p, n_tiles, st);
+    default: return launch_fwd<4>(p, n_tiles, st);
+  }
+}
+
+int gs3d_composite_sh_backward(uint32_t M, const float *records, const float *sh_coeffs,
+                               uint32_t sh_stride_g, uint32_t sh_stride_c, const int32_t *start,
+                               const int32_t *end, const int32_t *gaussian_ids, const float *out,
+                               const float *grad_out, float *grad_mean2d, float *grad_cov2d,
+                               float *grad_sh, uint32_t gsh_stride_g, uint32_t gsh_stride_c,
+                               float *grad_alpha, const float *topleft, const float *c2w,
+                               uint32_t tile_size, uint32_t n_tiles_h, uint32_t n_tiles_w,
+                               float pixel_size_x, float pixel_size_y, uint32_t H, uint32_t W,
+                               uint32_t C, float thresh, int exact_decisions, void *stream) {
+  (void)M;
+  GS3D_REQUIRE(tile_size == TILE, GS3D_EUNSUPPORTED,
+               "compositing kernels support tile_size 16 only (got %u)", tile_size);
+  GS3D_REQUIRE(C >= 1 && C <= 4, GS3D_EINVAL, "SH order C must be 1..4 (got %u)", C);
+  const uint32_t n_tiles = n_tiles_h * n_tiles_w;
+  if (n_tiles == 0 || H == 0 || W == 0) return GS3D_OK;
+  GS3D_REQUIRE(start && end && out && grad_out && grad_mean2d && grad_cov2d && grad_sh && grad_alpha &&
+                   topleft && c2w,
+               GS3D_EINVAL, "composite_sh_backward: null argument");
+  GS3D_REQUIRE(aligned16(records), GS3D_EINVAL, "records must be 16-byte aligned");
+  CompositeParams p = {};
+  p.records = reinterpret_cast<const float4 *>(records);
+  p.sh = sh_coeffs; p.sh_sg = sh_stride_g; p.sh_sc = sh_stride_c;
+  p.start = start; p.end = end; p.ids = gaussian_ids;
+  p.topleft = topleft; p.c2w = c2w;
+  p.ntw = n_tiles_w; p.nth = n_tiles_h; p.psx = pixel_size_x; p.psy = pixel_size_y;
+  p.H = H; p.W = W; p.thresh = thresh; p.exact = exact_decisions;
+  p.out_saved = out; p.grad_out = grad_out;
+  p.g_mean = grad_mean2d; p.g_cov = grad_cov2d; p.g_sh = grad_sh; p.g_alpha = grad_alpha;
+  p.gsh_sg = gsh_stride_g; p.gsh_sc = gsh_stride_c;
+  const uint32_t CC = C * C;
+  p.sh_vec = (CC % 4 == 0) && (sh_stride_g % 4 == 0) && (sh_stride_c % 4 == 0) && aligned16(sh_coeffs);
+  p.gsh_vec = (CC % 4 == 0) && (gsh_stride_g % 4 == 0) && (gsh_stride_c % 4 == 0) && aligned16(grad_sh);
+  cudaStream_t st = as_stream(stream);
+  switch (C) {
+    case 1: return launch_bwd<1>(p, n_tiles, st);
+    case 2: return launch_bwd<2>(p, n_tiles, st);
+    case 3: return launch_bwd<3>(p, n_tiles, st);
+    default: return launch_bwd<4>(p, n_tiles, st);
+  }
+}
+
+}  // extern "C"

@@ -1,0 +1,246 @@
+"""Tensor-level wrappers over the C ABI (capi).  Validation mirrors the reference's CHECK_* macros
+(gs/src/include/common.h:29-54): a wrong device / layout / dtype raises RuntimeError.  Scratch
+memory comes from torch's caching allocator (the reference cudaMalloc/cudaFree'd inside the call,
+aabb_culling.h:204-259).  Everything is enqueued on the current torch stream.
+"""
+import ctypes as C
+
+import torch
+
+from . import capi
+from .capi import check, ptr
+
+_F32, _I32, _BOOL, _U8, _I64 = torch.float32, torch.int32, torch.bool, torch.uint8, torch.int64
+
+
+def _chk(t, name, dtype):
+    if not isinstance(t, torch.Tensor):
+        raise RuntimeError(f"{name} must be a tensor")
+    if not t.is_cuda:
+        raise RuntimeError(f"{name} must be a CUDA tensor")
+    if not t.is_contiguous():
+        raise RuntimeError(f"{name} must be a contiguous tensor")
+    dts = dtype if isinstance(dtype, tuple) else (dtype,)
+    if t.dtype not in dts:
+        kind = {_F32: "a floating", _I32: "an int", _BOOL: "an bool"}.get(dts[0], str(dts[0]))
+        raise RuntimeError(f"{name} must be {kind} tensor")
+    return t
+
+
+def _stream(t):
+    return capi.current_stream(t.device)
+
+
+def _scratch(nbytes, device):
+    return torch.empty(max(int(nbytes), 256), dtype=_U8, device=device)
+
+
+# ---------------------------------------------------------------- a1
+def get_frustum(c2w, camera_info):
+    _chk(c2w, "c2w", _F32)
+    normals = torch.empty(6, 3, dtype=_F32, device=c2w.device)
+    pts = torch.empty(6, 3, dtype=_F32, device=c2w.device)
+    cam = capi.camera_struct(camera_info)
+    check(capi.lib.gs3d_get_frustum(ptr(c2w), C.byref(cam), ptr(normals), ptr(pts), _stream(c2w)),
+          "get_frustum")
+    return normals, pts
+
+
+# ---------------------------------------------------------------- a2
+def culling_gaussian_bsphere(mean, qvec, svec, normal, pts, mask, thresh):
+    for t, n in ((mean, "mean"), (qvec, "qvec"), (svec, "svec"), (normal, "normal"), (pts, "pts")):
+        _chk(t, n, _F32)
+    _chk(mask, "mask", _BOOL)
+    check(capi.lib.gs3d_culling_gaussian_bsphere(mean.size(0), ptr(mean), ptr(qvec), ptr(svec),
+                                                 ptr(normal), ptr(pts), ptr(mask), float(thresh),
+                                                 _stream(mean)), "culling_gaussian_bsphere")
+
+
+# ---------------------------------------------------------------- a4
+def project_gaussians_forward(mean, qvec, svec, c2w, want_JW=True):
+    for t, n in ((mean, "mean"), (qvec, "qvec"), (svec, "svec"), (c2w, "c2w")):
+        _chk(t, n, _F32)
+    N = mean.size(0)
+    dev = mean.device
+    mean2d = torch.empty(N, 2, dtype=_F32, device=dev)
+    cov = torch.empty(N, 2, 2, dtype=_F32, device=dev)
+    JW = torch.empty(N, 3, 3, dtype=_F32, device=dev) if want_JW else None
+    depth = torch.empty(N, 1, dtype=_F32, device=dev)
+    check(capi.lib.gs3d_project_gaussians(N, ptr(mean), ptr(qvec), ptr(svec), ptr(c2w), ptr(mean2d),
+                                          ptr(cov), ptr(JW), ptr(depth), _stream(mean)),
+          "project_gaussians")
+    return mean2d, cov, JW, depth
+
+
+def project_gaussians_backward(mean, qvec, svec, c2w, g_mean2d, g_cov, g_depth, detach_depth):
+    N = mean.size(0)
+    dev = mean.device
+    gm = torch.empty(N, 3, dtype=_F32, device=dev)
+    gq = torch.empty(N, 4, dtype=_F32, device=dev)
+    gs = torch.empty(N, 3, dtype=_F32, device=dev)
+    g_mean2d = _chk(g_mean2d.contiguous(), "grad_mean2d", _F32)
+    g_cov = _chk(g_cov.contiguous(), "grad_cov", _F32)
+    if g_depth is not None:
+        g_depth = _chk(g_depth.contiguous(), "grad_depth", _F32)
+    check(capi.lib.gs3d_project_gaussians_backward(N, ptr(mean), ptr(qvec), ptr(svec), ptr(c2w),
+                                                   ptr(g_mean2d), ptr(g_cov), ptr(g_depth),
+                                                   1 if detach_depth else 0, ptr(gm), ptr(gq),
+                                                   ptr(gs), _stream(mean)),
+          "project_gaussians_backward")
+    return gm, gq, gs
+
+
+# ---------------------------------------------------------------- a5
+def tile_culling_aabb_count(mean2d, cov, tile_size, camera_info, D):
+    _chk(mean2d, "mean", _F32)
+    _chk(cov, "cov", _F32)
+    N = mean2d.size(0)
+    dev = mean2d.device
+    tl = torch.empty(N, 2, dtype=_I32, device=dev)
+    br = torch.empty(N, 2, dtype=_I32, device=dev)
+    n = C.c_int64(0)
+    scratch = _scratch(capi.lib.gs3d_count_scratch_bytes(N), dev)
+    cam = capi.camera_struct(camera_info)
+    check(capi.lib.gs3d_tile_culling_aabb_count(N, ptr(mean2d), ptr(cov), int(tile_size),
+                                                C.byref(cam), float(D), ptr(tl), ptr(br),
+                                                C.byref(n), ptr(scratch), scratch.numel(),
+                                                _stream(mean2d)), "tile_culling_aabb_count")
+    return int(n.value), tl, br
+
+
+# ---------------------------------------------------------------- fused K1
+def project_cull_fused(mean, qvec, svec_param, alpha_param, svec_act, alpha_act, c2w, camera_info,
+                       frustum_radius, skip_frustum_culling, tile_D, tile_size, cnt=None,
+                       want_records=True, want_activated=True):
+    for t, n in ((mean, "mean"), (qvec, "qvec"), (svec_param, "svec"), (alpha_param, "alpha"),
+                 (c2w, "c2w")):
+        _chk(t, n, _F32)
+    if cnt is not None:
+        _chk(cnt, "cnt", _I32)
+    N = mean.size(0)
+    dev = mean.device
+    out = {
+        "mask": torch.empty(N, dtype=_BOOL, device=dev),
+        "mean2d": torch.empty(N, 2, dtype=_F32, device=dev),
+        "cov": torch.empty(N, 2, 2, dtype=_F32, device=dev),
+        "depth": torch.empty(N, 1, dtype=_F32, device=dev),
+        "tl": torch.empty(N, 2, dtype=_I32, device=dev),
+        "br": torch.empty(N, 2, dtype=_I32, device=dev),
+        "records": torch.empty(N, 12, dtype=_F32, device=dev) if want_records else None,
+        "svec": torch.empty(N, 3, dtype=_F32, device=dev) if want_activated else None,
+        "alpha": torch.empty(N, dtype=_F32, device=dev) if want_activated else None,
+    }
+    n = C.c_int64(0)
+    scratch = _scratch(256, dev)
+    cam = capi.camera_struct(camera_info)
+    check(capi.lib.gs3d_project_cull_fused(
+        N, ptr(mean), ptr(qvec), ptr(svec_param), ptr(alpha_param), int(svec_act), int(alpha_act),
+        ptr(c2w), C.byref(cam), float(frustum_radius), 1 if skip_frustum_culling else 0,
+        float(tile_D), int(tile_size), ptr(out["mask"]), ptr(out["mean2d"]), ptr(out["cov"]),
+        ptr(out["depth"]), ptr(out["tl"]), ptr(out["br"]), ptr(out["records"]), ptr(out["svec"]),
+        ptr(out["alpha"]), ptr(cnt), C.byref(n), ptr(scratch), scratch.numel(), _stream(mean)),
+        "project_cull_fused")
+    out["n_dub"] = int(n.value)
+    return out
+
+
+# ---------------------------------------------------------------- a6
+def tile_culling_aabb_start_end(aabb_topleft, aabb_bottomright, gaussian_ids, start, end, depth,
+                                n_tiles_h, n_tiles_w, sorted_keys=None, check_count=True):
+    for t, n in ((aabb_topleft, "aabb_topleft"), (aabb_bottomright, "aabb_bottomright"),
+                 (gaussian_ids, "gaussian_ids"), (start, "start"), (end, "end")):
+        _chk(t, n, _I32)
+    _chk(depth, "depth", _F32)
+    if sorted_keys is not None:
+        _chk(sorted_keys, "sorted_keys", _I64)
+    N = aabb_topleft.size(0)
+    n_dub = gaussian_ids.size(0)
+    if start.numel() < n_tiles_h * n_tiles_w or end.numel() < n_tiles_h * n_tiles_w:
+        raise RuntimeError("start/end must have n_tiles_h * n_tiles_w elements")
+    nbytes = capi.lib.gs3d_binning_scratch_bytes(N, n_dub)
+    scratch = _scratch(nbytes, depth.device)
+    check(capi.lib.gs3d_tile_culling_aabb_start_end(
+        N, n_dub, int(n_tiles_h), int(n_tiles_w), ptr(aabb_topleft), ptr(aabb_bottomright),
+        ptr(depth), ptr(gaussian_ids), ptr(start), ptr(end), ptr(sorted_keys),
+        1 if check_count else 0, ptr(scratch), scratch.numel(), _stream(depth)),
+        "tile_culling_aabb_start_end")
+
+
+# ---------------------------------------------------------------- records
+def pack_records(mean2d, cov, alpha, depth=None):
+    _chk(mean2d, "mean", _F32)
+    _chk(cov, "cov", _F32)
+    _chk(alpha, "alpha", _F32)
+    N = mean2d.size(0)
+    rec = torch.empty(N, 12, dtype=_F32, device=mean2d.device)
+    check(capi.lib.gs3d_pack_records(N, ptr(mean2d), ptr(cov), ptr(alpha), ptr(depth), ptr(rec),
+                                     _stream(mean2d)), "pack_records")
+    return rec
+
+
+def _sh_strides(sh, C):
+    """(stride per Gaussian, stride per channel) in floats for an [M,3,>=C*C] tensor whose last
+    dimension is dense; lets the fused path pass sh_coeffs[..., :C*C] without a copy."""
+    if sh.dim() != 3 or sh.size(1) != 3 or sh.size(2) < C * C or sh.stride(2) != 1:
+        raise RuntimeError("sh_coeffs must be [N,3,>=C*C] with a dense last dimension")
+    return sh.stride(0), sh.stride(1)
+
+
+# ---------------------------------------------------------------- a7 / a11
+def composite_sh_forward(records, sh, start, end, gaussian_ids, out, topleft, c2w, tile_size,
+                         n_tiles_h, n_tiles_w, pixel_size_x, pixel_size_y, H, W, C_, thresh,
+                         bg_rgb=None, final_T=None, n_contrib=None, exact=True):
+    _chk(records, "records", _F32)
+    for t, n in ((start, "start"), (end, "end"), (gaussian_ids, "gaussian_ids")):
+        _chk(t, n, _I32)
+    for t, n in ((out, "out"), (topleft, "topleft"), (c2w, "c2w")):
+        _chk(t, n, _F32)
+    if not sh.is_cuda or sh.dtype != _F32:
+        raise RuntimeError("sh_coeffs must be a CUDA floating tensor")
+    sg, sc = _sh_strides(sh, C_)
+    if out.numel() < H * W * 3:
+        raise RuntimeError("out must have H*W*3 elements")
+    check(capi.lib.gs3d_composite_sh_forward(
+        records.size(0), ptr(records), ptr(sh), sg, sc, ptr(start), ptr(end), ptr(gaussian_ids),
+        ptr(out), ptr(topleft), ptr(c2w), int(tile_size), int(n_tiles_h), int(n_tiles_w),
+        float(pixel_size_x), float(pixel_size_y), int(H), int(W), int(C_), float(thresh),
+        ptr(bg_rgb), ptr(final_T), ptr(n_contrib), 1 if exact else 0, _stream(out)),
+        "tile_based_vol_rendering_sh")
+
+
+# ---------------------------------------------------------------- a8 / a11
+def composite_sh_backward(records, sh, start, end, gaussian_ids, out, grad_out, grad_mean, grad_cov,
+                          grad_sh, grad_alpha, topleft, c2w, tile_size, n_tiles_h, n_tiles_w,
+                          pixel_size_x, pixel_size_y, H, W, C_, thresh, exact=True):
+    _chk(records, "records", _F32)
+    for t, n in ((start, "start"), (end, "end"), (gaussian_ids, "gaussian_ids")):
+        _chk(t, n, _I32)
+    for t, n in ((out, "out"), (grad_out, "grad_out"), (grad_mean, "grad_mean"),
+                 (grad_cov, "grad_cov"), (grad_alpha, "grad_alpha"), (topleft, "topleft"),
+                 (c2w, "c2w")):
+        _chk(t, n, _F32)
+    sg, sc = _sh_strides(sh, C_)
+    gsg, gsc = _sh_strides(grad_sh, C_)
+    check(capi.lib.gs3d_composite_sh_backward(
+        records.size(0), ptr(records), ptr(sh), sg, sc, ptr(start), ptr(end), ptr(gaussian_ids),
+        ptr(out), ptr(grad_out), ptr(grad_mean), ptr(grad_cov), ptr(grad_sh), gsg, gsc,
+        ptr(grad_alpha), ptr(topleft), ptr(c2w), int(tile_size), int(n_tiles_h), int(n_tiles_w),
+        float(pixel_size_x), float(pixel_size_y), int(H), int(W), int(C_), float(thresh),
+        1 if exact else 0, _stream(out)), "tile_based_vol_rendering_backward_sh")
+
+
+# ---------------------------------------------------------------- a9 + a10
+def project_backward_fused(mask, mean, qvec, svec_param, alpha_param, svec_act, alpha_act, c2w,
+                           detach_depth, g_mean2d, g_cov, g_alpha, grad_mean_acc=None, adc_mode=0):
+    N = mean.size(0)
+    dev = mean.device
+    gm = torch.empty(N, 3, dtype=_F32, device=dev)
+    gq = torch.empty(N, 4, dtype=_F32, device=dev)
+    gs = torch.empty(N, 3, dtype=_F32, device=dev)
+    ga = torch.empty(N, dtype=_F32, device=dev)
+    check(capi.lib.gs3d_project_backward_fused(
+        N, ptr(mask), ptr(mean), ptr(qvec), ptr(svec_param), ptr(alpha_param), int(svec_act),
+        int(alpha_act), ptr(c2w), 1 if detach_depth else 0, ptr(g_mean2d), ptr(g_cov), ptr(g_alpha),
+        ptr(gm), ptr(gq), ptr(gs), ptr(ga), ptr(grad_mean_acc), int(adc_mode), _stream(mean)),
+        "project_backward_fused")
+    return gm, gq, gs, ga

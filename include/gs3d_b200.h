@@ -1,0 +1,185 @@
+/*
+ * gs3d_b200.h -- C ABI of the B200-native Gaussian-splatting rasteriser (libgs3d_b200.so).
+ *
+ * This is the drop-in boundary for the hot path of heheyas/gaussian_splatting_3d: every entry
+ * point replaces one binding of the reference's `_gs` pybind module (gs/src/bindings.cpp:5-67,
+ * prototypes gs/src/render.h:3-131) or one torch-level function that sits between two bindings
+ * on the path (gs/renderer.py, gs/culling.py, utils/camera.py).  Plain pointers and sizes only:
+ * no torch types.  All pointers are DEVICE pointers unless the name ends in `_host`.
+ *
+ * Conventions
+ *   - every function returns 0 on success, else a GS3D_E* code; gs3d_last_error() gives the
+ *     message (thread-local).  Nothing calls exit() or traps (the reference printf+exit()s,
+ *     common.h:56-72).
+ *   - `stream` is a cudaStream_t passed as void*; all work is enqueued on it (the reference runs
+ *     its cull/bin kernels on the legacy stream and cudaMalloc/cudaFree/D2H-syncs inside,
+ *     aabb_culling.h:204-259; this library never allocates: scratch comes from the caller).
+ *   - outputs are written in place into caller-allocated buffers, like the reference.
+ *   - layouts are the reference's: mean [N,3], qvec [N,4] (w,x,y,z), svec [N,3], mean2d [N,2],
+ *     cov2d [N,4] row-major 2x2 with S01 and S10 kept apart, sh_coeffs channel-major
+ *     [N][3][C*C], image HWC float32, start/end int32 with -1 = empty tile, keys int64
+ *     (tile id << 32 | float32 depth bits).
+ *   - only tile_size == 16 is supported by the compositing kernels (all reference configs,
+ *     conf/ *.yaml `tile_size: 16`); other sizes return GS3D_EUNSUPPORTED.
+ */
+#ifndef GS3D_B200_H
+#define GS3D_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GS3D_OK 0
+#define GS3D_EINVAL 1       /* bad argument (null pointer, size mismatch, bad C) */
+#define GS3D_ECUDA 2        /* CUDA runtime / launch failure */
+#define GS3D_EUNSUPPORTED 3 /* valid in the reference, not implemented here (e.g. tile_size != 16) */
+#define GS3D_ECOUNT 4       /* emitted duplicate count != n_dub (reference: assert, aabb_culling.h:228) */
+
+/* Mirrors utils/camera.py:219-230 CameraInfo (intrinsics holder). */
+typedef struct gs3d_camera {
+  double fx, fy, cx, cy; /* Python floats in the reference; rounded to FP32 where torch would */
+  int32_t w, h;
+  double near_plane, far_plane;
+} gs3d_camera;
+
+/* Per-Gaussian staging record consumed by the compositing kernels: 12 floats = 48 B, 16-B aligned.
+ *   [0] mean2d.x  [1] mean2d.y  [2] min(alpha,0.99)  [3] log2((1/255)/alpha_) (skip threshold)
+ *   [4..6] -0.5*log2(e) * (c3, -(c1+c2), c0) / det   (fast conic form)   [7] depth
+ *   [8..11] c0 c1 c2 c3 (raw covariance; exact-decision path and backward)            */
+#define GS3D_RECORD_FLOATS 12
+
+int gs3d_version(void);
+const char *gs3d_last_error(void);
+
+/* ---- a1  CameraInfo.get_frustum, utils/camera.py:249-283.  c2w [3,4] device; normals/pts [6,3]. */
+int gs3d_get_frustum(const float *c2w, const gs3d_camera *cam_host, float *normals, float *pts,
+                     void *stream);
+
+/* ---- a2  culling_gaussian_bsphere, bindings.cpp:6 / render.cu:15-43 / culling.h:11-34.
+ * mask is torch.bool storage (1 byte per Gaussian). qvec is accepted and unused, as in the reference. */
+int gs3d_culling_gaussian_bsphere(uint32_t N, const float *mean, const float *qvec,
+                                  const float *svec, const float *normal, const float *pts,
+                                  uint8_t *mask, float thresh, void *stream);
+
+/* ---- a4  project_gaussians, gs/renderer.py:391-419 (+ :366-387, utils/transforms.py:31-45).
+ * JW [N,3,3] may be NULL.  depth [N].  Forward only; see gs3d_project_gaussians_backward. */
+int gs3d_project_gaussians(uint32_t N, const float *mean, const float *qvec, const float *svec,
+                           const float *c2w, float *mean2d, float *cov2d, float *JW, float *depth,
+                           void *stream);
+
+/* autograd of a4 (quirk Q6: J constant, depth detached unless detach_depth == 0).
+ * grad_depth may be NULL.  Outputs are OVERWRITTEN: grad_mean [N,3], grad_qvec [N,4],
+ * grad_svec [N,3]. */
+int gs3d_project_gaussians_backward(uint32_t N, const float *mean, const float *qvec,
+                                    const float *svec, const float *c2w, const float *grad_mean2d,
+                                    const float *grad_cov2d, const float *grad_depth,
+                                    int detach_depth, float *grad_mean, float *grad_qvec,
+                                    float *grad_svec, void *stream);
+
+/* ---- a5  tile_culling_aabb_count, gs/culling.py:8-37 + utils/camera.py:290-303 (quirk Q8).
+ * aabb_topleft / aabb_bottomright int32 [N,2] (tile units, inclusive).  The duplicate count is
+ * written to *n_dub_host after a stream synchronise (the reference's `.item()`, culling.py:33-35).
+ * scratch: >= gs3d_count_scratch_bytes(N) bytes of device memory. */
+size_t gs3d_count_scratch_bytes(uint32_t N);
+int gs3d_tile_culling_aabb_count(uint32_t N, const float *mean2d, const float *cov2d,
+                                 uint32_t tile_size, const gs3d_camera *cam_host, float D,
+                                 int32_t *aabb_topleft, int32_t *aabb_bottomright,
+                                 int64_t *n_dub_host, void *scratch, size_t scratch_bytes,
+                                 void *stream);
+
+/* ---- a2+a4+a5 fused (the product path; replaces sh_renderer.py:189-236 minus the mask
+ * compaction): frustum planes, sphere cull, activations (svec = exp, alpha = sigmoid when the
+ * *_act flags are 1; 0 = identity), projection, tile rect, duplicate count and staging record in
+ * ONE pass over the parameters.  Culled Gaussians get rect tl=(0,0) br=(-1,-1) (zero duplicates)
+ * and mask 0; nothing is compacted, ids stay original indices.
+ * Outputs: mask [N] u8, mean2d [N,2], cov2d [N,4], depth [N], aabb tl/br int32 [N,2],
+ * records [N,12] (may be NULL), svec_out [N,3] / alpha_out [N] activated values (may be NULL),
+ * cnt int32 [N] (may be NULL): cnt[i] += 1 for kept Gaussians (sh_renderer.py:215-216).
+ * *n_dub_host is valid after return (one 8-byte D2H + stream sync). */
+int gs3d_project_cull_fused(uint32_t N, const float *mean, const float *qvec,
+                            const float *svec_param, const float *alpha_param, int svec_act,
+                            int alpha_act, const float *c2w, const gs3d_camera *cam_host,
+                            float frustum_radius, int skip_frustum_culling, float tile_D,
+                            uint32_t tile_size, uint8_t *mask, float *mean2d, float *cov2d,
+                            float *depth, int32_t *aabb_topleft, int32_t *aabb_bottomright,
+                            float *records, float *svec_out, float *alpha_out, int32_t *cnt,
+                            int64_t *n_dub_host, void *scratch, size_t scratch_bytes, void *stream);
+
+/* ---- a6  tile_culling_aabb_start_end, bindings.cpp:27 / render.cu:380-397 /
+ * aabb_culling.h:15-41,70-103,192-260.  Hand-written LSD radix sort of the 64-bit key
+ * (tile << 32 | depth bits): the four depth-byte passes run over the N Gaussians BEFORE
+ * duplication, the tile-digit passes over the n_dub duplicates; the result equals a stable
+ * ascending int64 sort of the reference's keys with ties (same tile, same depth bits) in
+ * ascending Gaussian id -- one of the orders the reference's atomic emission can produce.
+ * gaussian_ids int32 [n_dub], start/end int32 [n_tiles] (-1 = empty), sorted_keys int64 [n_dub]
+ * optional (NULL to skip).  Returns GS3D_ECOUNT (after a sync) only when check_count != 0 and the
+ * rects do not add up to n_dub. */
+size_t gs3d_binning_scratch_bytes(uint32_t N, uint32_t n_dub);
+int gs3d_tile_culling_aabb_start_end(uint32_t N, uint32_t n_dub, uint32_t n_tiles_h,
+                                     uint32_t n_tiles_w, const int32_t *aabb_topleft,
+                                     const int32_t *aabb_bottomright, const float *depth,
+                                     int32_t *gaussian_ids, int32_t *start, int32_t *end,
+                                     int64_t *sorted_keys, int check_count, void *scratch,
+                                     size_t scratch_bytes, void *stream);
+
+/* ---- staging records from raw arrays (used by the reference-signature wrappers below). */
+int gs3d_pack_records(uint32_t N, const float *mean2d, const float *cov2d, const float *alpha,
+                      const float *depth /* may be NULL */, float *records, void *stream);
+
+/* ---- a7 / a11  tile_based_vol_rendering_sh{,_with_bg}, bindings.cpp:42,57 /
+ * render.cu:483-544 / vol_render_sh.h:97-266 / vol_render_bg.h:12-100.
+ * records [M,12]; sh_coeffs rows addressed as sh_coeffs + g*sh_stride_g + c*sh_stride_c + k
+ * (reference layout: sh_stride_g = 3*C*C, sh_stride_c = C*C).  topleft [2], c2w [3,4], bg_rgb [3]
+ * device pointers (bg_rgb NULL = no background).  out [H*W*3] is fully written for non-empty
+ * tiles; pixels of empty tiles are left untouched (caller pre-zeroes, renderer.py:693) or set to
+ * bg.  final_T [H*W] and n_contrib int32 [H*W] are optional extra outputs (NULL to skip).
+ * exact_decisions != 0 re-evaluates the Gaussian in the reference's exact FP32 operation order
+ * whenever alpha*G is within 2e-3 (relative) of the 1/255 skip threshold. */
+int gs3d_composite_sh_forward(uint32_t M, const float *records, const float *sh_coeffs,
+                              uint32_t sh_stride_g, uint32_t sh_stride_c, const int32_t *start,
+                              const int32_t *end, const int32_t *gaussian_ids, float *out,
+                              const float *topleft, const float *c2w, uint32_t tile_size,
+                              uint32_t n_tiles_h, uint32_t n_tiles_w, float pixel_size_x,
+                              float pixel_size_y, uint32_t H, uint32_t W, uint32_t C, float thresh,
+                              const float *bg_rgb, float *final_T, int32_t *n_contrib,
+                              int exact_decisions, void *stream);
+
+/* ---- a8 / a11  tile_based_vol_rendering_backward_sh{,_with_bg}, bindings.cpp:44,60 /
+ * render.cu:546-624 / vol_render_sh.h:268-480 / kernels.h:394-418.
+ * Gradients are ACCUMULATED (caller pre-zeroes, renderer.py:761-764): grad_mean2d [M,2],
+ * grad_cov2d [M,4], grad_alpha [M], grad_sh rows at grad_sh + g*gsh_stride_g + c*gsh_stride_c + k.
+ * out is the saved forward image.  Per-warp reduction in shared memory, one vector
+ * red.global.add per (tile, Gaussian) row instead of the reference's 256 shared atomics. */
+int gs3d_composite_sh_backward(uint32_t M, const float *records, const float *sh_coeffs,
+                               uint32_t sh_stride_g, uint32_t sh_stride_c, const int32_t *start,
+                               const int32_t *end, const int32_t *gaussian_ids, const float *out,
+                               const float *grad_out, float *grad_mean2d, float *grad_cov2d,
+                               float *grad_sh, uint32_t gsh_stride_g, uint32_t gsh_stride_c,
+                               float *grad_alpha, const float *topleft, const float *c2w,
+                               uint32_t tile_size, uint32_t n_tiles_h, uint32_t n_tiles_w,
+                               float pixel_size_x, float pixel_size_y, uint32_t H, uint32_t W,
+                               uint32_t C, float thresh, int exact_decisions, void *stream);
+
+/* ---- a9 + a10 fused: chain rule from (grad_mean2d, grad_cov2d, grad_alpha) to the leaf
+ * parameters through projection (Q6) and the activations (sh_renderer.py:318-324), for the
+ * Gaussians with mask != 0 (others get zero gradient; mask NULL = all), plus the ADC accumulator
+ * of sh_renderer.py:602-623: when adc_mode != 0,
+ * grad_mean_acc[i] = max(., ||grad_mean2d_i||) (adc_mode 1, split_reduction "max") or
+ * += ||grad_mean2d_i|| (adc_mode 2, "mean") for split_type "2d_mean_grad".
+ * Leaf gradients are OVERWRITTEN. */
+int gs3d_project_backward_fused(uint32_t N, const uint8_t *mask, const float *mean,
+                                const float *qvec, const float *svec_param,
+                                const float *alpha_param, int svec_act, int alpha_act,
+                                const float *c2w, int detach_depth, const float *grad_mean2d,
+                                const float *grad_cov2d, const float *grad_alpha,
+                                float *grad_mean, float *grad_qvec, float *grad_svec_param,
+                                float *grad_alpha_param, float *grad_mean_acc, int adc_mode,
+                                void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GS3D_B200_H */
