@@ -35,6 +35,7 @@ _I64P = C.POINTER(C.c_int64)
 SIGNATURES = {
     "gs3d_version": (_i, []),
     "gs3d_last_error": (C.c_char_p, []),
+    "gs3d_launch_count": (C.c_uint64, []),
     "gs3d_get_frustum": (_i, [_P, _CAM, _P, _P, _P]),
     "gs3d_culling_gaussian_bsphere": (_i, [_u32, _P, _P, _P, _P, _P, _P, _f, _P]),
     "gs3d_project_gaussians": (_i, [_u32, _P, _P, _P, _P, _P, _P, _P, _P, _P]),

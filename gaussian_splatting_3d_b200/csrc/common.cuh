@@ -14,6 +14,7 @@ namespace gs3d {
 
 // thread-local error slot (gs3d_last_error)
 void set_error(const char *fmt, ...);
+void count_launch();
 
 #define GS3D_REQUIRE(cond, code, ...)      \
   do {                                     \
@@ -32,7 +33,12 @@ void set_error(const char *fmt, ...);
     }                                                                                         \
   } while (0)
 
-#define GS3D_LAUNCH_CHECK() GS3D_CUDA(cudaGetLastError())
+// every kernel launch goes through this macro: counts launches (gs3d_launch_count) and checks
+#define GS3D_LAUNCH_CHECK()          \
+  do {                               \
+    gs3d::count_launch();            \
+    GS3D_CUDA(cudaGetLastError());   \
+  } while (0)
 
 static inline cudaStream_t as_stream(void *s) { return reinterpret_cast<cudaStream_t>(s); }
 

@@ -19,6 +19,9 @@ void set_error(const char *fmt, ...) {
   va_end(ap);
 }
 
+static unsigned long long g_launches = 0;
+void count_launch() { __atomic_fetch_add(&g_launches, 1ull, __ATOMIC_RELAXED); }
+
 int64_t *pinned_mailbox() {
   static thread_local int64_t *box = nullptr;
   if (!box) {
@@ -524,6 +527,7 @@ extern "C" {
 
 int gs3d_version(void) { return 100; }
 const char *gs3d_last_error(void) { return g_err; }
+uint64_t gs3d_launch_count(void) { return __atomic_load_n(&g_launches, __ATOMIC_RELAXED); }
 
 int gs3d_get_frustum(const float *c2w, const gs3d_camera *cam_host, float *normals, float *pts,
                      void *stream) {

@@ -53,6 +53,8 @@ typedef struct gs3d_camera {
 
 int gs3d_version(void);
 const char *gs3d_last_error(void);
+/* number of CUDA kernels this library has launched in this process (bench.py's gpu_launches) */
+uint64_t gs3d_launch_count(void);
 
 /* ---- a1  CameraInfo.get_frustum, utils/camera.py:249-283.  c2w [3,4] device; normals/pts [6,3]. */
 int gs3d_get_frustum(const float *c2w, const gs3d_camera *cam_host, float *normals, float *pts,
