@@ -1,0 +1,187 @@
+"""Multi-GPU paths (new capability: the reference has no distributed code).
+One process per GPU, torch.distributed (NCCL on GPUs, gloo in the CPU tests) for the plumbing.
+
+(i)  View-sharded training (cfg 4): parameters replicated, each rank renders its share of the
+     step's cameras forward+backward, gradients are summed with ONE all-reduce over a flat buffer
+     that the parameters' `.grad`s alias (236 B/Gaussian at C = 4); the ADC statistics follow
+     (grad_mean: sum or max; cnt: sum).
+(ii) Tile-sharded rendering (cfg 5): projection is replicated (cheap), each rank bins and
+     composites one band of tile rows -- bands balanced by per-row duplicate counts -- and the
+     bands are gathered into the full frame.  No reduction is needed: tiles are independent.
+"""
+import torch
+import torch.distributed as dist
+
+_PARAMS = ("mean", "qvec", "svec_before_activation", "sh_coeffs", "alpha_before_activation")
+
+
+class FlatGradients:
+    """Allocates one flat FP32 buffer and points every parameter's .grad at a slice of it."""
+
+    def __init__(self, module):
+        self.params = [getattr(module, n) for n in _PARAMS]
+        total = sum(p.numel() for p in self.params)
+        self.flat = torch.zeros(total, dtype=torch.float32, device=self.params[0].device)
+        self.views = []
+        off = 0
+        for p in self.params:
+            v = self.flat[off:off + p.numel()].view_as(p)
+            p.grad = v
+            self.views.append(v)
+            off += p.numel()
+
+    def zero(self):
+        self.flat.zero_()
+        for p, v in zip(self.params, self.views):
+            p.grad = v  # optimisers / zero_grad(set_to_none) may have dropped the alias
+
+    def all_reduce(self, group=None, average=False):
+        if dist.is_initialized() and dist.get_world_size(group) > 1:
+            dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=group)
+            if average:
+                self.flat.div_(dist.get_world_size(group))
+        return self.flat
+
+
+def shard_views(n_views, rank, world):
+    """Indices of the step's cameras rendered by `rank` (round-robin; 8 cameras over 1/2/4/8 ranks)."""
+    return list(range(rank, n_views, world))
+
+
+def view_sharded_step(renderer, flat, c2ws, camera_info, targets, loss_fn=None, group=None):
+    """One data-parallel training step over `c2ws` (the whole step's cameras, same list on every
+    rank).  Returns this rank's summed loss tensor.  After the call every rank holds the SUM of the
+    gradients over all cameras in the parameters' .grad (and in flat.flat)."""
+    rank = dist.get_rank(group) if dist.is_initialized() else 0
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    if loss_fn is None:
+        loss_fn = lambda out, tgt: ((out - tgt) ** 2).mean()  # noqa: E731
+    flat.zero()
+    total = None
+    for i in shard_views(len(c2ws), rank, world):
+        out = renderer(c2ws[i], camera_info)
+        loss = loss_fn(out, targets[i])
+        loss.backward()  # accumulates into the aliased flat buffer
+        total = loss.detach() if total is None else total + loss.detach()
+    flat.all_reduce(group)
+    sync_adc(renderer, group)
+    return total
+
+
+def sync_adc(renderer, group=None):
+    """Make the ADC statistics identical on all ranks (sh_renderer.py:602-623 semantics over the
+    union of the step's views): cnt is summed; grad_mean is summed ('mean') or max-reduced ('max').
+    Each rank contributes only what it accumulated since the last sync."""
+    if not (dist.is_initialized() and dist.get_world_size(group) > 1):
+        return
+    if not hasattr(renderer, "_adc_synced"):
+        renderer._adc_synced = (torch.zeros_like(renderer.grad_mean), torch.zeros_like(renderer.cnt))
+    gm0, cnt0 = renderer._adc_synced
+    d_cnt = renderer.cnt - cnt0
+    dist.all_reduce(d_cnt, op=dist.ReduceOp.SUM, group=group)
+    renderer.cnt = cnt0 + d_cnt
+    if renderer.split_reduction == "max":
+        gm = renderer.grad_mean.clone()
+        dist.all_reduce(gm, op=dist.ReduceOp.MAX, group=group)
+    else:
+        d_gm = renderer.grad_mean - gm0
+        dist.all_reduce(d_gm, op=dist.ReduceOp.SUM, group=group)
+        gm = gm0 + d_gm
+    renderer.grad_mean = gm
+    renderer._adc_synced = (gm.clone(), renderer.cnt.clone())
+
+
+# ---------------------------------------------------------------- tile-sharded rendering
+
+
+def row_duplicate_counts(aabb_topleft, aabb_bottomright, n_tiles_h):
+    """Duplicates per tile row from the per-Gaussian rects (int64 [n_tiles_h]); difference array +
+    prefix sum, integer arithmetic only, so every rank computes the same numbers."""
+    tl, br = aabb_topleft.long(), aabb_bottomright.long()
+    w = (br[:, 0] - tl[:, 0] + 1).clamp_(min=0)
+    valid = (br[:, 1] >= tl[:, 1]) & (w > 0)
+    w = w * valid
+    diff = torch.zeros(n_tiles_h + 1, dtype=torch.long, device=tl.device)
+    diff.index_add_(0, tl[:, 1].clamp(0, n_tiles_h), w)
+    diff.index_add_(0, (br[:, 1] + 1).clamp(0, n_tiles_h), -w)
+    return torch.cumsum(diff, 0)[:n_tiles_h]
+
+
+def balanced_bands(row_counts, world):
+    """Split tile rows into `world` contiguous bands with near-equal duplicate totals.
+    -> list of (row_begin, row_end) covering [0, n_rows) in order; empty bands allowed."""
+    rc = row_counts.tolist()
+    n = len(rc)
+    total = sum(rc)
+    bounds = [0]
+    acc, r = 0, 0
+    for k in range(1, world):
+        target = total * k / world
+        while r < n and acc + rc[r] / 2 <= target:
+            acc += rc[r]
+            r += 1
+        bounds.append(max(r, bounds[-1]))
+    bounds.append(n)
+    return [(bounds[i], bounds[i + 1]) for i in range(world)]
+
+
+def clip_rects_to_band(aabb_topleft, aabb_bottomright, row_begin, row_end):
+    """Restrict rects to tile rows [row_begin, row_end); rects outside become empty (br < tl)."""
+    tl = aabb_topleft.clone()
+    br = aabb_bottomright.clone()
+    tl[:, 1].clamp_(min=row_begin)
+    br[:, 1].clamp_(max=row_end - 1)
+    n = ((br[:, 0] - tl[:, 0] + 1).clamp(min=0).long() * (br[:, 1] - tl[:, 1] + 1).clamp(min=0).long()).sum()
+    return tl, br, n
+
+
+@torch.no_grad()
+def tile_sharded_render(renderer, c2w, camera_info, group=None, gather=True):
+    """Render one frame with tile rows sharded over the ranks of `group` (forward only).
+    Every rank returns the full [H,W,3] image when gather=True, else its band ([rows,W,3], row0)."""
+    from . import ops
+
+    rank = dist.get_rank(group) if dist.is_initialized() else 0
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    dev = renderer.mean.device
+    cam, tile, C = camera_info, renderer.tile_size, renderer.now_C
+    k1 = ops.project_cull_fused(
+        renderer.mean.data, renderer.qvec.data, renderer.svec_before_activation.data,
+        renderer.alpha_before_activation.data, renderer._svec_code, renderer._alpha_code,
+        c2w.contiguous().float(), cam, renderer.frustum_culling_radius, renderer.skip_frustum_culling,
+        renderer.tile_culling_radius, tile, cnt=None, want_records=True, want_activated=False)
+    H, W = cam.h, cam.w
+    nth = H // tile + (H % tile > 0)
+    ntw = W // tile + (W % tile > 0)
+    bands = balanced_bands(row_duplicate_counts(k1["tl"], k1["br"], nth), world)
+    r0, r1 = bands[rank]
+    tl, br, n_band = clip_rects_to_band(k1["tl"], k1["br"], r0, r1)
+    n_band = int(n_band.item())
+    ids = torch.empty(n_band, dtype=torch.int32, device=dev)
+    start = torch.empty(nth * ntw, dtype=torch.int32, device=dev)
+    end = torch.empty(nth * ntw, dtype=torch.int32, device=dev)
+    ops.tile_culling_aabb_start_end(tl, br, ids, start, end, k1["depth"], nth, ntw, check_count=False)
+    out = torch.zeros(H * W * 3, dtype=torch.float32, device=dev)
+    topleft = torch.tensor([-cam.cx / cam.fx, -cam.cy / cam.fy], dtype=torch.float32).to(dev)
+    bg = renderer.bg_rgb if renderer.bg else None
+    ops.composite_sh_forward(k1["records"], renderer.sh_coeffs.data, start, end, ids, out, topleft,
+                             c2w.contiguous().float(), tile, nth, ntw, 1.0 / cam.fx, 1.0 / cam.fy, H, W, C,
+                             renderer.T_thresh, bg_rgb=bg, exact=renderer.exact_decisions)
+    img = out.view(H, W, 3)
+    y0, y1 = r0 * tile, min(r1 * tile, H)
+    if world == 1 or not gather:
+        return img if world == 1 else (img[y0:y1], y0)
+    if bg is not None:
+        # rows outside the band were filled with bg by the empty-tile rule; keep only the band
+        pass
+    # equal-size padded bands so that one all_gather_into_tensor moves everything
+    max_rows = max((min(b * tile, H) - a * tile) for a, b in bands)
+    send = torch.zeros(max_rows, W, 3, dtype=torch.float32, device=dev)
+    send[: y1 - y0] = img[y0:y1]
+    recv = torch.empty(world * max_rows, W, 3, dtype=torch.float32, device=dev)
+    dist.all_gather_into_tensor(recv, send, group=group)
+    full = torch.empty(H, W, 3, dtype=torch.float32, device=dev)
+    for k, (a, b) in enumerate(bands):
+        ya, yb = a * tile, min(b * tile, H)
+        full[ya:yb] = recv[k * max_rows: k * max_rows + (yb - ya)]
+    return full

@@ -1,0 +1,107 @@
+"""CPU tests of the multi-GPU host logic: band partitioning for tile-sharded rendering and the
+flat-gradient all-reduce of view-sharded training over a world_size-2 gloo group."""
+import os
+
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from gaussian_splatting_3d_b200 import parallel as P
+
+
+def test_row_counts_and_bands_cover_everything():
+    g = torch.Generator().manual_seed(0)
+    n, nth, ntw = 5000, 53, 82
+    tlx = torch.randint(0, ntw, (n,), generator=g)
+    tly = torch.randint(0, nth, (n,), generator=g)
+    brx = torch.minimum(tlx + torch.randint(0, 5, (n,), generator=g), torch.tensor(ntw - 1))
+    bry = torch.minimum(tly + torch.randint(0, 5, (n,), generator=g), torch.tensor(nth - 1))
+    tl = torch.stack([tlx, tly], 1).int()
+    br = torch.stack([brx, bry], 1).int()
+    tl[::11] = torch.tensor([0, 0], dtype=torch.int32)  # culled-style empty rects
+    br[::11] = torch.tensor([-1, -1], dtype=torch.int32)
+    rc = P.row_duplicate_counts(tl, br, nth)
+    # brute force
+    want = torch.zeros(nth, dtype=torch.long)
+    for i in range(n):
+        w = int(br[i, 0] - tl[i, 0] + 1)
+        for y in range(int(tl[i, 1]), int(br[i, 1]) + 1):
+            want[y] += w
+    assert torch.equal(rc, want)
+    total = int(((br[:, 0] - tl[:, 0] + 1).clamp(min=0).long() * (br[:, 1] - tl[:, 1] + 1).clamp(min=0).long()).sum())
+    assert int(rc.sum()) == total
+    for world in (1, 2, 3, 4, 8):
+        bands = P.balanced_bands(rc, world)
+        assert len(bands) == world and bands[0][0] == 0 and bands[-1][1] == nth
+        assert all(bands[i][1] == bands[i + 1][0] for i in range(world - 1))
+        parts = []
+        for a, b in bands:
+            tlc, brc, nb = P.clip_rects_to_band(tl, br, a, b)
+            parts.append(int(nb))
+            assert int(nb) == int(rc[a:b].sum())
+        assert sum(parts) == total
+        if world > 1:
+            assert max(parts) <= total / world + int(rc.max())  # balanced to within one row
+
+
+def _worker(rank, world, port, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+
+    class M(torch.nn.Module):
+        pass
+
+    m = M()
+    g = torch.Generator().manual_seed(7)
+    n = 50
+    m.mean = torch.nn.Parameter(torch.randn(n, 3, generator=g))
+    m.qvec = torch.nn.Parameter(torch.randn(n, 4, generator=g))
+    m.svec_before_activation = torch.nn.Parameter(torch.randn(n, 3, generator=g))
+    m.sh_coeffs = torch.nn.Parameter(torch.randn(n, 3, 4, generator=g))
+    m.alpha_before_activation = torch.nn.Parameter(torch.randn(n, generator=g))
+    m.split_reduction = "mean"
+    m.grad_mean = torch.zeros(n)
+    m.cnt = torch.zeros(n, dtype=torch.int32)
+    flat = P.FlatGradients(m)
+    flat.zero()
+    views = P.shard_views(8, rank, world)
+    # a stand-in "renderer": loss depends on the view index so ranks contribute different gradients
+    for v in views:
+        loss = sum(((p * (v + 1)) ** 2).sum() for p in flat.params)
+        loss.backward()
+        m.grad_mean += float(v + 1)
+        m.cnt += 1
+    flat.all_reduce()
+    P.sync_adc(m)
+    q.put((rank, views, flat.flat.clone(), m.grad_mean.clone(), m.cnt.clone(),
+           [p.grad.data_ptr() == vw.data_ptr() for p, vw in zip(flat.params, flat.views)]))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_view_sharded_gradient_allreduce_gloo_world2():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + (os.getpid() % 2000)
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted([q.get(timeout=120) for _ in range(2)], key=lambda t: t[0])
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    (r0, v0, f0, gm0, c0, al0), (r1, v1, f1, gm1, c1, al1) = res
+    assert v0 == [0, 2, 4, 6] and v1 == [1, 3, 5, 7]
+    assert all(al0) and all(al1)  # .grad aliases the flat buffer
+    assert torch.equal(f0, f1)  # every rank holds the same summed gradient
+    # single-process reference: sum over all 8 views
+    g = torch.Generator().manual_seed(7)
+    n = 50
+    ps = [torch.randn(n, 3, generator=g), torch.randn(n, 4, generator=g), torch.randn(n, 3, generator=g),
+          torch.randn(n, 3, 4, generator=g), torch.randn(n, generator=g)]
+    scale = sum(2.0 * (v + 1) ** 2 for v in range(8))
+    want = torch.cat([(p * scale).reshape(-1) for p in ps])
+    assert torch.allclose(f0, want, rtol=1e-5, atol=1e-5)
+    assert torch.equal(gm0, gm1) and float(gm0[0]) == float(sum(range(1, 9)))
+    assert torch.equal(c0, c1) and int(c0[0]) == 8
