@@ -405,12 +405,25 @@ def run_reference(args, rank, local_rank, world):
         torch.cuda.synchronize()
         return e0.elapsed_time(e1)
 
-    for _ in range(max(args.warmup, 3)):
-        step(True)
-    with ClockSampler(phys_gpu_index(local_rank)) as clk:
-        ms = timed(lambda: step(False), args.steps)
-        ms_e2e = timed(lambda: step(True), args.steps)
-        ms_fwd = timed(fwd_only, args.steps)
+    # The reference's backward printf()s from the device whenever its recomputed image differs
+    # from the saved one (vol_render_sh.h:448-451); keep that out of our single JSON line.
+    sys.stdout.flush()
+    saved_fd = os.dup(1)
+    devnull = os.open(os.devnull, os.O_WRONLY)
+    os.dup2(devnull, 1)
+    try:
+        for _ in range(max(args.warmup, 3)):
+            step(True)
+        with ClockSampler(phys_gpu_index(local_rank)) as clk:
+            ms = timed(lambda: step(False), args.steps)
+            ms_e2e = timed(lambda: step(True), args.steps)
+            ms_fwd = timed(fwd_only, args.steps)
+        torch.cuda.synchronize()
+    finally:
+        sys.stdout.flush()
+        os.dup2(saved_fd, 1)
+        os.close(devnull)
+        os.close(saved_fd)
     base.update({
         "value": 1000.0 * args.steps / ms, "ms_per_step": ms / args.steps,
         "fwd_fps": 1000.0 * args.steps / ms_fwd,

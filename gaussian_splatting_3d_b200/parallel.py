@@ -136,26 +136,26 @@ def clip_rects_to_band(aabb_topleft, aabb_bottomright, row_begin, row_end):
 
 
 @torch.no_grad()
-def tile_sharded_render(renderer, c2w, camera_info, group=None, gather=True):
-    """Render one frame with tile rows sharded over the ranks of `group` (forward only).
-    Every rank returns the full [H,W,3] image when gather=True, else its band ([rows,W,3], row0)."""
+def render_band(renderer, c2w, camera_info, row_begin=None, row_end=None, k1=None):
+    """Forward-render tile rows [row_begin, row_end) of one frame (None = all rows).  Returns the
+    full-size [H,W,3] buffer in which only the band's rows are written, plus the K1 outputs."""
     from . import ops
 
-    rank = dist.get_rank(group) if dist.is_initialized() else 0
-    world = dist.get_world_size(group) if dist.is_initialized() else 1
     dev = renderer.mean.device
     cam, tile, C = camera_info, renderer.tile_size, renderer.now_C
-    k1 = ops.project_cull_fused(
-        renderer.mean.data, renderer.qvec.data, renderer.svec_before_activation.data,
-        renderer.alpha_before_activation.data, renderer._svec_code, renderer._alpha_code,
-        c2w.contiguous().float(), cam, renderer.frustum_culling_radius, renderer.skip_frustum_culling,
-        renderer.tile_culling_radius, tile, cnt=None, want_records=True, want_activated=False)
+    c2w = c2w.contiguous().float()
+    if k1 is None:
+        k1 = ops.project_cull_fused(
+            renderer.mean.data, renderer.qvec.data, renderer.svec_before_activation.data,
+            renderer.alpha_before_activation.data, renderer._svec_code, renderer._alpha_code, c2w, cam,
+            renderer.frustum_culling_radius, renderer.skip_frustum_culling, renderer.tile_culling_radius, tile,
+            cnt=None, want_records=True, want_activated=False)
     H, W = cam.h, cam.w
     nth = H // tile + (H % tile > 0)
     ntw = W // tile + (W % tile > 0)
-    bands = balanced_bands(row_duplicate_counts(k1["tl"], k1["br"], nth), world)
-    r0, r1 = bands[rank]
-    tl, br, n_band = clip_rects_to_band(k1["tl"], k1["br"], r0, r1)
+    if row_begin is None:
+        row_begin, row_end = 0, nth
+    tl, br, n_band = clip_rects_to_band(k1["tl"], k1["br"], row_begin, row_end)
     n_band = int(n_band.item())
     ids = torch.empty(n_band, dtype=torch.int32, device=dev)
     start = torch.empty(nth * ntw, dtype=torch.int32, device=dev)
@@ -164,16 +164,37 @@ def tile_sharded_render(renderer, c2w, camera_info, group=None, gather=True):
     out = torch.zeros(H * W * 3, dtype=torch.float32, device=dev)
     topleft = torch.tensor([-cam.cx / cam.fx, -cam.cy / cam.fy], dtype=torch.float32).to(dev)
     bg = renderer.bg_rgb if renderer.bg else None
-    ops.composite_sh_forward(k1["records"], renderer.sh_coeffs.data, start, end, ids, out, topleft,
-                             c2w.contiguous().float(), tile, nth, ntw, 1.0 / cam.fx, 1.0 / cam.fy, H, W, C,
-                             renderer.T_thresh, bg_rgb=bg, exact=renderer.exact_decisions)
-    img = out.view(H, W, 3)
+    ops.composite_sh_forward(k1["records"], renderer.sh_coeffs.data, start, end, ids, out, topleft, c2w, tile,
+                             nth, ntw, 1.0 / cam.fx, 1.0 / cam.fy, H, W, C, renderer.T_thresh, bg_rgb=bg,
+                             exact=renderer.exact_decisions)
+    return out.view(H, W, 3), k1
+
+
+@torch.no_grad()
+def tile_sharded_render(renderer, c2w, camera_info, group=None, gather=True):
+    """Render one frame with tile rows sharded over the ranks of `group` (forward only).
+    Every rank returns the full [H,W,3] image when gather=True, else (its band [rows,W,3], row0)."""
+    from . import ops
+
+    rank = dist.get_rank(group) if dist.is_initialized() else 0
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    dev = renderer.mean.device
+    cam, tile = camera_info, renderer.tile_size
+    H, W = cam.h, cam.w
+    nth = H // tile + (H % tile > 0)
+    k1 = ops.project_cull_fused(
+        renderer.mean.data, renderer.qvec.data, renderer.svec_before_activation.data,
+        renderer.alpha_before_activation.data, renderer._svec_code, renderer._alpha_code,
+        c2w.contiguous().float(), cam, renderer.frustum_culling_radius, renderer.skip_frustum_culling,
+        renderer.tile_culling_radius, tile, cnt=None, want_records=True, want_activated=False)
+    bands = balanced_bands(row_duplicate_counts(k1["tl"], k1["br"], nth), world)
+    r0, r1 = bands[rank]
+    img, _ = render_band(renderer, c2w, cam, r0, r1, k1=k1)
     y0, y1 = r0 * tile, min(r1 * tile, H)
-    if world == 1 or not gather:
-        return img if world == 1 else (img[y0:y1], y0)
-    if bg is not None:
-        # rows outside the band were filled with bg by the empty-tile rule; keep only the band
-        pass
+    if world == 1:
+        return img
+    if not gather:
+        return img[y0:y1], y0
     # equal-size padded bands so that one all_gather_into_tensor moves everything
     max_rows = max((min(b * tile, H) - a * tile) for a, b in bands)
     send = torch.zeros(max_rows, W, 3, dtype=torch.float32, device=dev)
