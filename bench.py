@@ -178,14 +178,13 @@ def run_ours(args, rank, local_rank, world):
     c2w_dev = c2w_host.to(dev)
     tgt_dev = tgt_host.to(dev)
     params = [r.mean, r.qvec, r.svec_before_activation, r.sh_coeffs, r.alpha_before_activation]
-    flat_grad = None
+    flat = None
     if world > 1:
-        # one flat gradient buffer (views as .grad) so the exchange is a single all-reduce
-        flat_grad = torch.zeros(sum(p.numel() for p in params), device=dev)
-        off = 0
-        for p in params:
-            p.grad = flat_grad[off:off + p.numel()].view_as(p)
-            off += p.numel()
+        # one flat gradient buffer that the backward kernels write into directly (no packing copy),
+        # summed over the ranks with a single NCCL all-reduce per step
+        from gaussian_splatting_3d_b200 import parallel as P
+
+        flat = P.FlatGradients(r).attach(r)
 
     def step(e2e):
         if e2e:
@@ -196,12 +195,9 @@ def run_ours(args, rank, local_rank, world):
         out = r(c2w, cam)
         loss = ((out - tgt) ** 2).mean()
         if world > 1:
-            gm, gq, gs, gsh, ga = torch.autograd.grad(loss, params)
-            off = 0
-            for g in (gm, gq, gs, gsh, ga):
-                flat_grad[off:off + g.numel()].copy_(g.reshape(-1))
-                off += g.numel()
-            dist.all_reduce(flat_grad)
+            flat.zero()
+            flat.backward_into(loss)
+            flat.all_reduce()
         else:
             for p in params:
                 p.grad = None

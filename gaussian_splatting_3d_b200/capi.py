@@ -54,7 +54,7 @@ SIGNATURES = {
                                         _u32, _u32, _P, _P, _P, _u32, _u32, _u32, _f, _f, _u32, _u32,
                                         _u32, _f, _i, _P]),
     "gs3d_project_backward_fused": (_i, [_u32, _P, _P, _P, _P, _P, _i, _i, _P, _i, _P, _P, _P, _P, _P,
-                                         _P, _P, _P, _i, _P]),
+                                         _P, _P, _P, _i, _i, _P]),
 }
 
 

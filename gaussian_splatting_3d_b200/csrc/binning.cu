@@ -11,6 +11,8 @@
 //
 // One radix pass = per-block digit histogram -> digit-major exclusive scan -> stable scatter staged
 // through shared memory so global writes are runs of consecutive addresses.  HBM-bound.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace gs3d {
@@ -84,7 +86,8 @@ radix_scan_kernel(uint32_t nblocks, uint32_t *__restrict__ table, const uint32_t
   }
 }
 
-__global__ void __launch_bounds__(SORT_THREADS)
+template <bool BALLOT_RANK>
+__global__ void __launch_bounds__(SORT_THREADS, 3)
 radix_scatter_kernel(const uint32_t *__restrict__ keys_in, const uint32_t *__restrict__ vals_in,
                      uint32_t *__restrict__ keys_out, uint32_t *__restrict__ vals_out, uint32_t n,
                      int shift, uint32_t mask, uint32_t nblocks,
@@ -93,6 +96,7 @@ radix_scatter_kernel(const uint32_t *__restrict__ keys_in, const uint32_t *__res
   __shared__ uint32_t s_vals[SORT_TILE];
   __shared__ uint32_t warp_hist[SORT_WARPS][RADIX];  // per-warp running digit counts
   __shared__ uint32_t digit_base[RADIX];             // exclusive scan of block digit totals
+  __shared__ uint32_t out_base[RADIX];               // global base - local base per digit
   __shared__ uint32_t warp_sums[SORT_WARPS];
 
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -103,30 +107,47 @@ radix_scatter_kernel(const uint32_t *__restrict__ keys_in, const uint32_t *__res
   // warp-striped tile: warp w owns items [w*512, (w+1)*512), item (i, lane) = w*512 + i*32 + lane
   const size_t tile_base = (size_t)blockIdx.x * SORT_TILE;
   const size_t warp_base = tile_base + (size_t)warp * (32 * SORT_IPT);
-  uint32_t k[SORT_IPT], v[SORT_IPT];
+  uint32_t k[SORT_IPT];
   uint16_t rank[SORT_IPT];
 #pragma unroll
   for (int i = 0; i < SORT_IPT; ++i) {
     size_t e = warp_base + (size_t)i * 32 + lane;
-    bool valid = e < n;
-    k[i] = valid ? keys_in[e] : 0xffffffffu;
-    v[i] = valid ? vals_in[e] : 0u;
+    k[i] = (e < n) ? keys_in[e] : 0xffffffffu;
   }
-  // stable rank inside the warp chunk, in (i, lane) order
+  // Stable rank inside the warp chunk, in (i, lane) order.  All 16 MATCH.ANY are issued first
+  // (independent, pipelined); the serial part is only the per-digit running counter update.
+  uint32_t peers[SORT_IPT];
 #pragma unroll
   for (int i = 0; i < SORT_IPT; ++i) {
-    size_t e = warp_base + (size_t)i * 32 + lane;
-    bool valid = e < n;
-    uint32_t active = __ballot_sync(0xffffffffu, valid);
-    uint32_t r = 0;
-    if (valid) {
-      uint32_t d = (k[i] >> shift) & mask;
-      uint32_t peers = __match_any_sync(active, d);
-      uint32_t before = warp_hist[warp][d];
-      r = before + __popc(peers & lt_mask);
-      __syncwarp(active);
-      if ((peers & lt_mask) == 0) warp_hist[warp][d] = before + __popc(peers);
+    const size_t e = warp_base + (size_t)i * 32 + lane;
+    const bool valid = e < n;
+    const uint32_t active = __ballot_sync(0xffffffffu, valid);
+    const uint32_t d = (k[i] >> shift) & mask;
+    if (BALLOT_RANK) {
+      // lanes with the same digit via one ballot per digit bit: MATCH.ANY serialises over the
+      // distinct values in the warp (~28 for random bytes), eight VOTEs do not
+      uint32_t m = active;
+#pragma unroll
+      for (int b = 0; b < RADIX_BITS; ++b) {
+        const uint32_t vote = __ballot_sync(0xffffffffu, (d >> b) & 1u);
+        m &= ((d >> b) & 1u) ? vote : ~vote;
+      }
+      peers[i] = valid ? m : 0u;
+    } else {
+      peers[i] = valid ? __match_any_sync(active, d) : 0u;
     }
+  }
+#pragma unroll
+  for (int i = 0; i < SORT_IPT; ++i) {
+    uint32_t r = 0;
+    const uint32_t d = (k[i] >> shift) & mask;
+    uint32_t before = 0;
+    if (peers[i]) {
+      before = warp_hist[warp][d];
+      r = before + __popc(peers[i] & lt_mask);
+    }
+    __syncwarp();
+    if (peers[i] && (peers[i] & lt_mask) == 0) warp_hist[warp][d] = before + __popc(peers[i]);
     __syncwarp();
     rank[i] = (uint16_t)r;
   }
@@ -153,6 +174,9 @@ radix_scatter_kernel(const uint32_t *__restrict__ keys_in, const uint32_t *__res
     uint32_t wb = 0;
     for (int w = 0; w < warp; ++w) wb += warp_sums[w];
     digit_base[d] = wb + incl - run;
+    // global position of the block's first item of digit d, minus its block-local position:
+    // the write-out loop then needs no dependent global load
+    out_base[d] = table[(size_t)d * nblocks + blockIdx.x] - (wb + incl - run);
   }
   __syncthreads();
   // place items at their block-local sorted position
@@ -163,7 +187,7 @@ radix_scatter_kernel(const uint32_t *__restrict__ keys_in, const uint32_t *__res
       uint32_t d = (k[i] >> shift) & mask;
       uint32_t lp = digit_base[d] + warp_hist[warp][d] + rank[i];
       s_keys[lp] = k[i];
-      s_vals[lp] = v[i];
+      s_vals[lp] = vals_in[e];  // payload goes straight from global to its sorted slot
     }
   }
   __syncthreads();
@@ -174,7 +198,165 @@ radix_scatter_kernel(const uint32_t *__restrict__ keys_in, const uint32_t *__res
     if (lp < n_here) {
       uint32_t key = s_keys[lp];
       uint32_t d = (key >> shift) & mask;
-      uint32_t pos = table[(size_t)d * nblocks + blockIdx.x] + (lp - digit_base[d]);
+      uint32_t pos = out_base[d] + lp;
+      keys_out[pos] = key;
+      vals_out[pos] = s_vals[lp];
+    }
+  }
+}
+
+// ---------------------------------------------------------------- onesweep pass
+// Single-kernel radix pass (Adinets & Merrill, "Onesweep", 2022): the global digit histograms of all
+// passes are computed up front in one read of the keys; each block then ranks its tile, publishes its
+// per-digit counts and obtains its global offsets by decoupled look-back over the preceding tiles.
+// Tiles are handed out by an atomic ticket, so every tile a block waits on is already running.
+
+constexpr uint32_t OS_FLAG_AGG = 1u << 30;     // tile's own digit count is published
+constexpr uint32_t OS_FLAG_PREFIX = 2u << 30;  // inclusive prefix (all tiles up to this one) is published
+constexpr uint32_t OS_VALUE_MASK = (1u << 30) - 1u;
+
+__global__ void __launch_bounds__(SORT_THREADS)
+multi_hist_kernel(const uint32_t *__restrict__ keys, uint32_t n, int shift0, int n_pass,
+                  uint32_t *__restrict__ hist /*[n_pass][RADIX]*/) {
+  __shared__ uint32_t h[4][RADIX];
+  for (int p = 0; p < n_pass; ++p) h[p][threadIdx.x] = 0;
+  __syncthreads();
+  const size_t base = (size_t)blockIdx.x * SORT_TILE;
+#pragma unroll 4
+  for (int i = 0; i < SORT_IPT; ++i) {
+    const size_t e = base + (size_t)i * SORT_THREADS + threadIdx.x;
+    if (e < n) {
+      const uint32_t k = keys[e] >> shift0;
+      for (int p = 0; p < n_pass; ++p) atomicAdd(&h[p][(k >> (RADIX_BITS * p)) & (RADIX - 1)], 1u);
+    }
+  }
+  __syncthreads();
+  for (int p = 0; p < n_pass; ++p) {
+    const uint32_t c = h[p][threadIdx.x];
+    if (c) atomicAdd(&hist[p * RADIX + threadIdx.x], c);
+  }
+}
+
+__device__ __forceinline__ uint32_t block_exclusive_scan_digits(uint32_t x, uint32_t *warp_sums) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  uint32_t incl = x;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    uint32_t y = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl += y;
+  }
+  __syncthreads();  // warp_sums may still be read from a previous call
+  if (lane == 31) warp_sums[warp] = incl;
+  __syncthreads();
+  uint32_t wb = 0;
+  for (int w = 0; w < warp; ++w) wb += warp_sums[w];
+  return wb + incl - x;
+}
+
+__global__ void __launch_bounds__(SORT_THREADS, 3)
+radix_onesweep_kernel(const uint32_t *__restrict__ keys_in, const uint32_t *__restrict__ vals_in,
+                      uint32_t *__restrict__ keys_out, uint32_t *__restrict__ vals_out, uint32_t n,
+                      int shift, const uint32_t *__restrict__ ghist /*[RADIX] digit totals*/,
+                      volatile uint32_t *status /*[tiles][RADIX], zeroed*/, uint32_t *ticket) {
+  __shared__ uint32_t s_keys[SORT_TILE];
+  __shared__ uint32_t s_vals[SORT_TILE];
+  __shared__ uint32_t warp_hist[SORT_WARPS][RADIX];
+  __shared__ uint32_t digit_base[RADIX];
+  __shared__ uint32_t out_base[RADIX];
+  __shared__ uint32_t warp_sums[SORT_WARPS];
+  __shared__ uint32_t s_tile;
+
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const uint32_t lt_mask = (1u << lane) - 1u;
+  const uint32_t mask = RADIX - 1;
+  if (threadIdx.x == 0) s_tile = atomicAdd(ticket, 1u);
+  for (int i = threadIdx.x; i < SORT_WARPS * RADIX; i += SORT_THREADS) (&warp_hist[0][0])[i] = 0;
+  __syncthreads();
+  const uint32_t tile = s_tile;
+
+  const size_t tile_base = (size_t)tile * SORT_TILE;
+  const size_t warp_base = tile_base + (size_t)warp * (32 * SORT_IPT);
+  uint32_t k[SORT_IPT];
+  uint16_t rank[SORT_IPT];
+#pragma unroll
+  for (int i = 0; i < SORT_IPT; ++i) {
+    size_t e = warp_base + (size_t)i * 32 + lane;
+    k[i] = (e < n) ? keys_in[e] : 0xffffffffu;
+  }
+  uint32_t peers[SORT_IPT];
+#pragma unroll
+  for (int i = 0; i < SORT_IPT; ++i) {
+    const size_t e = warp_base + (size_t)i * 32 + lane;
+    const bool valid = e < n;
+    const uint32_t active = __ballot_sync(0xffffffffu, valid);
+    peers[i] = valid ? __match_any_sync(active, (k[i] >> shift) & mask) : 0u;
+  }
+#pragma unroll
+  for (int i = 0; i < SORT_IPT; ++i) {
+    uint32_t r = 0;
+    const uint32_t d = (k[i] >> shift) & mask;
+    uint32_t before = 0;
+    if (peers[i]) {
+      before = warp_hist[warp][d];
+      r = before + __popc(peers[i] & lt_mask);
+    }
+    __syncwarp();
+    if (peers[i] && (peers[i] & lt_mask) == 0) warp_hist[warp][d] = before + __popc(peers[i]);
+    __syncwarp();
+    rank[i] = (uint16_t)r;
+  }
+  __syncthreads();
+  {
+    const int d = threadIdx.x;
+    uint32_t run = 0;
+#pragma unroll
+    for (int w = 0; w < SORT_WARPS; ++w) {
+      uint32_t c = warp_hist[w][d];
+      warp_hist[w][d] = run;
+      run += c;
+    }
+    // publish this tile's digit count as early as possible
+    volatile uint32_t *mine = status + (size_t)tile * RADIX + d;
+    *mine = (tile == 0 ? OS_FLAG_PREFIX : OS_FLAG_AGG) | run;
+    const uint32_t local_base = block_exclusive_scan_digits(run, warp_sums);
+    const uint32_t gstart = block_exclusive_scan_digits(ghist[d], warp_sums);
+    // decoupled look-back over the preceding tiles
+    uint32_t excl = 0;
+    if (tile != 0) {
+      int tt = (int)tile - 1;
+      while (true) {
+        uint32_t v;
+        do {
+          v = status[(size_t)tt * RADIX + d];
+        } while ((v >> 30) == 0);
+        excl += v & OS_VALUE_MASK;
+        if ((v >> 30) == 2 || tt == 0) break;
+        --tt;
+      }
+      *mine = OS_FLAG_PREFIX | (excl + run);
+    }
+    digit_base[d] = local_base;
+    out_base[d] = gstart + excl - local_base;
+  }
+  __syncthreads();
+#pragma unroll
+  for (int i = 0; i < SORT_IPT; ++i) {
+    size_t e = warp_base + (size_t)i * 32 + lane;
+    if (e < n) {
+      uint32_t d = (k[i] >> shift) & mask;
+      uint32_t lp = digit_base[d] + warp_hist[warp][d] + rank[i];
+      s_keys[lp] = k[i];
+      s_vals[lp] = vals_in[e];
+    }
+  }
+  __syncthreads();
+  const uint32_t n_here = (uint32_t)min((size_t)SORT_TILE, (size_t)n - tile_base);
+#pragma unroll 4
+  for (int i = 0; i < SORT_IPT; ++i) {
+    uint32_t lp = i * SORT_THREADS + threadIdx.x;
+    if (lp < n_here) {
+      uint32_t key = s_keys[lp];
+      uint32_t pos = out_base[(key >> shift) & mask] + lp;
       keys_out[pos] = key;
       vals_out[pos] = s_vals[lp];
     }
@@ -182,9 +364,41 @@ radix_scatter_kernel(const uint32_t *__restrict__ keys_in, const uint32_t *__res
 }
 
 struct RadixBuffers {
-  uint32_t *table;   // [RADIX][nblocks_max]
-  uint32_t *totals;  // [RADIX]
+  uint32_t *table;   // [RADIX][nblocks_max]  (classic: per-block digit counts; onesweep: tile status)
+  uint32_t *totals;  // [8][RADIX]  (classic uses row 0; onesweep: one histogram per pass) + tickets
 };
+
+// Both passes sort identically and measure the same on cfg 2 (0.64 vs 0.65 ms for the whole binning):
+// the three-kernel pass stays the default because it has no inter-block spin-wait.
+static bool use_onesweep() {
+  static const int v = [] {
+    const char *e = getenv("GS3D_SORT");
+    return (e && e[0] == 'o') ? 1 : 0;  // GS3D_SORT=onesweep selects the single-kernel look-back pass
+  }();
+  return v != 0;
+}
+
+// histograms of `n_pass` consecutive 8-bit digits starting at bit `shift0`, rows [row0, row0+n_pass)
+static int onesweep_histograms(const uint32_t *keys, uint32_t n, int shift0, int n_pass, int row0,
+                               const RadixBuffers &rb, cudaStream_t st) {
+  GS3D_CUDA(cudaMemsetAsync(rb.totals + row0 * RADIX, 0, (size_t)n_pass * RADIX * sizeof(uint32_t), st));
+  multi_hist_kernel<<<div_up(n, (uint32_t)SORT_TILE), SORT_THREADS, 0, st>>>(keys, n, shift0, n_pass,
+                                                                            rb.totals + row0 * RADIX);
+  GS3D_LAUNCH_CHECK();
+  return GS3D_OK;
+}
+
+static int onesweep_pass(const uint32_t *kin, const uint32_t *vin, uint32_t *kout, uint32_t *vout,
+                         uint32_t n, int shift, int hist_row, const RadixBuffers &rb, cudaStream_t st) {
+  const uint32_t nblocks = div_up(n, (uint32_t)SORT_TILE);
+  uint32_t *ticket = rb.totals + 8 * RADIX;
+  GS3D_CUDA(cudaMemsetAsync(rb.table, 0, (size_t)nblocks * RADIX * sizeof(uint32_t), st));
+  GS3D_CUDA(cudaMemsetAsync(ticket, 0, sizeof(uint32_t), st));
+  radix_onesweep_kernel<<<nblocks, SORT_THREADS, 0, st>>>(kin, vin, kout, vout, n, shift,
+                                                          rb.totals + hist_row * RADIX, rb.table, ticket);
+  GS3D_LAUNCH_CHECK();
+  return GS3D_OK;
+}
 
 static int radix_pass(const uint32_t *kin, const uint32_t *vin, uint32_t *kout, uint32_t *vout,
                       uint32_t n, int shift, int bits, const RadixBuffers &rb, cudaStream_t st) {
@@ -195,8 +409,13 @@ static int radix_pass(const uint32_t *kin, const uint32_t *vin, uint32_t *kout, 
   GS3D_LAUNCH_CHECK();
   radix_scan_kernel<<<RADIX, 256, 0, st>>>(nblocks, rb.table, rb.totals);
   GS3D_LAUNCH_CHECK();
-  radix_scatter_kernel<<<nblocks, SORT_THREADS, 0, st>>>(kin, vin, kout, vout, n, shift, mask, nblocks,
-                                                         rb.table);
+  static const bool ballot = [] { const char *e = getenv("GS3D_RANK"); return !(e && e[0] == 'm'); }();
+  if (ballot)
+    radix_scatter_kernel<true><<<nblocks, SORT_THREADS, 0, st>>>(kin, vin, kout, vout, n, shift, mask,
+                                                                 nblocks, rb.table);
+  else
+    radix_scatter_kernel<false><<<nblocks, SORT_THREADS, 0, st>>>(kin, vin, kout, vout, n, shift, mask,
+                                                                  nblocks, rb.table);
   GS3D_LAUNCH_CHECK();
   return GS3D_OK;
 }
@@ -379,7 +598,7 @@ size_t gs3d_binning_scratch_bytes(uint32_t N, uint32_t n_dub) {
   b += 4 * align_up((size_t)N * 4);                                   // depth keys/vals ping-pong
   b += align_up((size_t)div_up(N ? N : 1u, 256u) * 4);                // block sums
   b += align_up((size_t)table_elems(N > n_dub ? N : n_dub) * 4);      // digit table
-  b += align_up(RADIX * 4) + 256;                                     // totals + total
+  b += align_up((8 * RADIX + 64) * 4) + 256;                          // histograms/totals + ticket + total
   b += 3 * align_up((size_t)n_dub * 4);                               // dup keys x2, vals x1
   return b + 1024;
 }
@@ -413,7 +632,7 @@ int gs3d_tile_culling_aabb_start_end(uint32_t N, uint32_t n_dub, uint32_t n_tile
   uint32_t *block_sums = sc.take<uint32_t>(nb256);
   RadixBuffers rb;
   rb.table = sc.take<uint32_t>(table_elems(N > n_dub ? N : n_dub));
-  rb.totals = sc.take<uint32_t>(RADIX);
+  rb.totals = sc.take<uint32_t>(8 * RADIX + 64);
   uint32_t *total = sc.take<uint32_t>(64);
   uint32_t *dK0 = sc.take<uint32_t>(n_dub), *dK1 = sc.take<uint32_t>(n_dub);
   uint32_t *dV0 = sc.take<uint32_t>(n_dub);
@@ -424,9 +643,19 @@ int gs3d_tile_culling_aabb_start_end(uint32_t N, uint32_t n_dub, uint32_t n_tile
   // 1. depth-byte passes over the Gaussians (low 32 bits of the reference key)
   init_depth_keys_kernel<<<nb256, 256, 0, st>>>(N, depth, kA, vA);
   GS3D_LAUNCH_CHECK();
+  const bool onesweep = use_onesweep();
+  if (onesweep) {
+    int rc = onesweep_histograms(kA, N, 0, 4, 0, rb, st);
+    if (rc) return rc;
+  }
   for (int p = 0; p < 4; ++p) {
-    int rc = (p & 1) ? radix_pass(kB, vB, kA, vA, N, 8 * p, 8, rb, st)
-                     : radix_pass(kA, vA, kB, vB, N, 8 * p, 8, rb, st);
+    int rc;
+    if (onesweep)
+      rc = (p & 1) ? onesweep_pass(kB, vB, kA, vA, N, 8 * p, p, rb, st)
+                   : onesweep_pass(kA, vA, kB, vB, N, 8 * p, p, rb, st);
+    else
+      rc = (p & 1) ? radix_pass(kB, vB, kA, vA, N, 8 * p, 8, rb, st)
+                   : radix_pass(kA, vA, kB, vB, N, 8 * p, 8, rb, st);
     if (rc) return rc;
   }
   // 2. deterministic offsets: scan of per-Gaussian duplicate counts in depth order
@@ -457,10 +686,15 @@ int gs3d_tile_culling_aabb_start_end(uint32_t N, uint32_t n_dub, uint32_t n_tile
   emit_kernel<<<nb256, 256, 0, st>>>(N, n_dub, n_tiles_w, vA, aabb_topleft, aabb_bottomright,
                                      block_sums, kcur, vcur);
   GS3D_LAUNCH_CHECK();
+  if (onesweep && n_pass > 0) {
+    int rc = onesweep_histograms(kcur, n_dub, 0, n_pass, 4, rb, st);
+    if (rc) return rc;
+  }
   for (int p = 0; p < n_pass; ++p) {
     int bits = tile_bits - p * RADIX_BITS;
     if (bits > RADIX_BITS) bits = RADIX_BITS;
-    int rc = radix_pass(kcur, vcur, knext, vnext, n_dub, p * RADIX_BITS, bits, rb, st);
+    int rc = onesweep ? onesweep_pass(kcur, vcur, knext, vnext, n_dub, p * RADIX_BITS, 4 + p, rb, st)
+                      : radix_pass(kcur, vcur, knext, vnext, n_dub, p * RADIX_BITS, bits, rb, st);
     if (rc) return rc;
     uint32_t *t = kcur; kcur = knext; knext = t;
     t = vcur; vcur = vnext; vnext = t;

@@ -319,7 +319,8 @@ __global__ void __launch_bounds__(256)
 project_cull_fused_kernel(uint32_t N, const float *__restrict__ mean,
                           const float *__restrict__ qvec, const float *__restrict__ svec_param,
                           const float *__restrict__ alpha_param, int svec_act, int alpha_act,
-                          const float *__restrict__ c2w_g, CamConst cam, float frustum_radius,
+                          const float *__restrict__ c2w_g, const float *__restrict__ planes_g,
+                          CamConst cam, float frustum_radius,
                           int skip_cull, float tile_D, int tile, uint8_t *__restrict__ mask,
                           float *__restrict__ mean2d, float *__restrict__ cov2d,
                           float *__restrict__ depth, int32_t *__restrict__ tl,
@@ -328,11 +329,11 @@ project_cull_fused_kernel(uint32_t N, const float *__restrict__ mean,
                           int32_t *__restrict__ cnt, unsigned long long *__restrict__ total) {
   __shared__ float c2w[12];
   __shared__ float planes[36];
+  // frustum planes come from frustum_kernel (one thread, once per frame), not from every CTA
   if (threadIdx.x < 12) c2w[threadIdx.x] = c2w_g[threadIdx.x];
+  else if (threadIdx.x >= 32 && threadIdx.x < 68) planes[threadIdx.x - 32] = planes_g[threadIdx.x - 32];
   __syncthreads();
-  if (threadIdx.x == 0) frustum_planes(c2w, cam, planes, planes + 18);
-  __syncthreads();
-  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   unsigned long long n_dup = 0;
   if (i < N) {
     float p[3] = {mean[3 * (size_t)i], mean[3 * (size_t)i + 1], mean[3 * (size_t)i + 2]};
@@ -463,7 +464,7 @@ project_backward_kernel(uint32_t N, const uint8_t *__restrict__ mask,
                         const float *__restrict__ gdepth, const float *__restrict__ galpha,
                         float *__restrict__ gmean, float *__restrict__ gqvec,
                         float *__restrict__ gsvec, float *__restrict__ galpha_param,
-                        float *__restrict__ adc_acc, int adc_mode) {
+                        float *__restrict__ adc_acc, int adc_mode, int accumulate) {
   __shared__ float c2w[12];
   if (threadIdx.x < 12) c2w[threadIdx.x] = c2w_g[threadIdx.x];
   __syncthreads();
@@ -503,6 +504,15 @@ project_backward_kernel(uint32_t N, const uint8_t *__restrict__ mask,
     g.gp[0] = g.gp[1] = g.gp[2] = 0.f;
     g.gq[0] = g.gq[1] = g.gq[2] = g.gq[3] = 0.f;
     g.gs[0] = g.gs[1] = g.gs[2] = 0.f;
+  }
+  if (accumulate) {  // several views per step: sum into the caller's gradient buffers
+    if (!keep) return;
+    gmean[3 * (size_t)i] += g.gp[0]; gmean[3 * (size_t)i + 1] += g.gp[1]; gmean[3 * (size_t)i + 2] += g.gp[2];
+    float4 q0 = reinterpret_cast<float4 *>(gqvec)[i];
+    reinterpret_cast<float4 *>(gqvec)[i] = make_float4(q0.x + g.gq[0], q0.y + g.gq[1], q0.z + g.gq[2], q0.w + g.gq[3]);
+    gsvec[3 * (size_t)i] += g.gs[0]; gsvec[3 * (size_t)i + 1] += g.gs[1]; gsvec[3 * (size_t)i + 2] += g.gs[2];
+    if (galpha_param) galpha_param[i] += ga;
+    return;
   }
   gmean[3 * (size_t)i] = g.gp[0]; gmean[3 * (size_t)i + 1] = g.gp[1]; gmean[3 * (size_t)i + 2] = g.gp[2];
   reinterpret_cast<float4 *>(gqvec)[i] = make_float4(g.gq[0], g.gq[1], g.gq[2], g.gq[3]);
@@ -573,7 +583,7 @@ int gs3d_project_gaussians_backward(uint32_t N, const float *mean, const float *
                GS3D_EINVAL, "gs3d_project_gaussians_backward: null argument");
   project_backward_kernel<<<div_up(N, 256u), 256, 0, as_stream(stream)>>>(
       N, nullptr, mean, qvec, svec, nullptr, 0, 0, c2w, detach_depth, grad_mean2d, grad_cov2d,
-      grad_depth, nullptr, grad_mean, grad_qvec, grad_svec, nullptr, nullptr, 0);
+      grad_depth, nullptr, grad_mean, grad_qvec, grad_svec, nullptr, nullptr, 0, 0);
   GS3D_LAUNCH_CHECK();
   return GS3D_OK;
 }
@@ -622,8 +632,8 @@ int gs3d_project_cull_fused(uint32_t N, const float *mean, const float *qvec,
                             float *depth, int32_t *aabb_topleft, int32_t *aabb_bottomright,
                             float *records, float *svec_out, float *alpha_out, int32_t *cnt,
                             int64_t *n_dub_host, void *scratch, size_t scratch_bytes, void *stream) {
-  GS3D_REQUIRE(cam_host && n_dub_host && scratch && scratch_bytes >= 8 && tile_size > 0 && c2w,
-               GS3D_EINVAL, "gs3d_project_cull_fused: bad argument");
+  GS3D_REQUIRE(cam_host && n_dub_host && scratch && scratch_bytes >= 256 && tile_size > 0 && c2w,
+               GS3D_EINVAL, "gs3d_project_cull_fused: bad argument (scratch must be >= 256 bytes)");
   cudaStream_t st = as_stream(stream);
   unsigned long long *total = static_cast<unsigned long long *>(scratch);
   GS3D_CUDA(cudaMemsetAsync(total, 0, 8, st));
@@ -631,8 +641,11 @@ int gs3d_project_cull_fused(uint32_t N, const float *mean, const float *qvec,
     GS3D_REQUIRE(mean && qvec && svec_param && alpha_param && mask && mean2d && cov2d && depth &&
                      aabb_topleft && aabb_bottomright,
                  GS3D_EINVAL, "gs3d_project_cull_fused: null argument");
+    float *planes = reinterpret_cast<float *>(static_cast<char *>(scratch) + 64);  // 36 floats
+    frustum_kernel<<<1, 32, 0, st>>>(c2w, make_cam(cam_host), planes, planes + 18);
+    GS3D_LAUNCH_CHECK();
     project_cull_fused_kernel<<<div_up(N, 256u), 256, 0, st>>>(
-        N, mean, qvec, svec_param, alpha_param, svec_act, alpha_act, c2w, make_cam(cam_host),
+        N, mean, qvec, svec_param, alpha_param, svec_act, alpha_act, c2w, planes, make_cam(cam_host),
         frustum_radius, skip_frustum_culling, tile_D, (int)tile_size, mask, mean2d, cov2d, depth,
         aabb_topleft, aabb_bottomright, records, svec_out, alpha_out, cnt, total);
     GS3D_LAUNCH_CHECK();
@@ -647,7 +660,7 @@ int gs3d_project_backward_fused(uint32_t N, const uint8_t *mask, const float *me
                                 const float *grad_cov2d, const float *grad_alpha,
                                 float *grad_mean, float *grad_qvec, float *grad_svec_param,
                                 float *grad_alpha_param, float *grad_mean_acc, int adc_mode,
-                                void *stream) {
+                                int accumulate, void *stream) {
   if (N == 0) return GS3D_OK;
   GS3D_REQUIRE(mean && qvec && svec_param && alpha_param && c2w && grad_mean2d && grad_cov2d &&
                    grad_alpha && grad_mean && grad_qvec && grad_svec_param && grad_alpha_param,
@@ -655,7 +668,7 @@ int gs3d_project_backward_fused(uint32_t N, const uint8_t *mask, const float *me
   project_backward_kernel<<<div_up(N, 256u), 256, 0, as_stream(stream)>>>(
       N, mask, mean, qvec, svec_param, alpha_param, svec_act, alpha_act, c2w, detach_depth,
       grad_mean2d, grad_cov2d, nullptr, grad_alpha, grad_mean, grad_qvec, grad_svec_param,
-      grad_alpha_param, grad_mean_acc, adc_mode);
+      grad_alpha_param, grad_mean_acc, adc_mode, accumulate);
   GS3D_LAUNCH_CHECK();
   return GS3D_OK;
 }

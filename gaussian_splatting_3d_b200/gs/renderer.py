@@ -198,14 +198,22 @@ class _splat_sh(torch.autograd.Function):
         g_mean2d = torch.zeros(N, 2, dtype=torch.float32, device=dev)
         g_cov = torch.zeros(N, 4, dtype=torch.float32, device=dev)
         g_alpha = torch.zeros(N, dtype=torch.float32, device=dev)
-        g_sh = torch.zeros(sh.shape, dtype=torch.float32, device=dev)
+        st = ctx.state
+        bufs = st.get("grad_buffers")  # caller-owned leaf-gradient buffers (views of a flat buffer)
+        if bufs is not None:
+            g_sh = bufs["sh_coeffs"]  # accumulated into: zeroed by the owner once per step
+            leaf_out = (bufs["mean"], bufs["qvec"], bufs["svec_before_activation"],
+                        bufs["alpha_before_activation"])
+        else:
+            g_sh = torch.zeros(sh.shape, dtype=torch.float32, device=dev)
+            leaf_out = None
         ops.composite_sh_backward(records, sh, start, end, ids, out, grad_out.contiguous().view(-1),
                                   g_mean2d, g_cov, g_sh, g_alpha, topleft, c2w, tile, nth, ntw, psx,
                                   psy, H, W, C, thresh, exact=exact)
-        st = ctx.state
         gm, gq, gs, ga = ops.project_backward_fused(
             mask, mean, qvec, svec_p, alpha_p, svec_act, alpha_act, c2w, detach, g_mean2d, g_cov,
-            g_alpha, grad_mean_acc=st.get("adc_acc"), adc_mode=st.get("adc_mode", 0))
+            g_alpha, grad_mean_acc=st.get("adc_acc"), adc_mode=st.get("adc_mode", 0), out=leaf_out,
+            accumulate=leaf_out is not None)
         st["grad_mean2d"] = g_mean2d
         ref = st.get("mean2d_ref")
         if ref is not None:  # sh_renderer.py:217-221 `mean_2d.retain_grad()` equivalent

@@ -85,6 +85,9 @@ class SHRenderer(torch.nn.Module):
         self.radius = None
         self.total_dub_gaussians = 0
         self.fuse_adc = False  # accumulate grad_mean inside the backward kernel (see update_grads)
+        # Optional caller-owned leaf-gradient buffers {param name: tensor}: backward ADDS into them
+        # instead of allocating (parallel.FlatGradients); use torch.autograd.grad, not .backward().
+        self.grad_buffers = None
         self._state = None
         if hasattr(self, "mean"):
             self._reset_adc_buffers(register=True)
@@ -182,6 +185,7 @@ class SHRenderer(torch.nn.Module):
             "cnt": self.cnt if hasattr(self, "cnt") else None,
             "bg_rgb": self.bg_rgb if self.bg else None, "exact": self.exact_decisions,
             "adc_acc": self.grad_mean if adc_mode else None, "adc_mode": adc_mode,
+            "grad_buffers": self.grad_buffers,
         }
         out = splat_sh(self.mean, self.qvec, self.svec_before_activation, self.sh_coeffs,
                        self.alpha_before_activation, c2w, state)

@@ -231,16 +231,25 @@ def composite_sh_backward(records, sh, start, end, gaussian_ids, out, grad_out, 
 
 # ---------------------------------------------------------------- a9 + a10
 def project_backward_fused(mask, mean, qvec, svec_param, alpha_param, svec_act, alpha_act, c2w,
-                           detach_depth, g_mean2d, g_cov, g_alpha, grad_mean_acc=None, adc_mode=0):
+                           detach_depth, g_mean2d, g_cov, g_alpha, grad_mean_acc=None, adc_mode=0,
+                           out=None, accumulate=False):
+    """`out` = (grad_mean, grad_qvec, grad_svec_param, grad_alpha_param) caller buffers (e.g. views of
+    one flat all-reduce buffer); with accumulate=True the kernel adds into them."""
     N = mean.size(0)
     dev = mean.device
-    gm = torch.empty(N, 3, dtype=_F32, device=dev)
-    gq = torch.empty(N, 4, dtype=_F32, device=dev)
-    gs = torch.empty(N, 3, dtype=_F32, device=dev)
-    ga = torch.empty(N, dtype=_F32, device=dev)
+    if out is None:
+        gm = torch.empty(N, 3, dtype=_F32, device=dev)
+        gq = torch.empty(N, 4, dtype=_F32, device=dev)
+        gs = torch.empty(N, 3, dtype=_F32, device=dev)
+        ga = torch.empty(N, dtype=_F32, device=dev)
+        accumulate = False
+    else:
+        gm, gq, gs, ga = out
+        for t, n in ((gm, "grad_mean"), (gq, "grad_qvec"), (gs, "grad_svec"), (ga, "grad_alpha")):
+            _chk(t, n, _F32)
     check(capi.lib.gs3d_project_backward_fused(
         N, ptr(mask), ptr(mean), ptr(qvec), ptr(svec_param), ptr(alpha_param), int(svec_act),
         int(alpha_act), ptr(c2w), 1 if detach_depth else 0, ptr(g_mean2d), ptr(g_cov), ptr(g_alpha),
-        ptr(gm), ptr(gq), ptr(gs), ptr(ga), ptr(grad_mean_acc), int(adc_mode), _stream(mean)),
-        "project_backward_fused")
+        ptr(gm), ptr(gq), ptr(gs), ptr(ga), ptr(grad_mean_acc), int(adc_mode), 1 if accumulate else 0,
+        _stream(mean)), "project_backward_fused")
     return gm, gq, gs, ga

@@ -16,9 +16,16 @@ _PARAMS = ("mean", "qvec", "svec_before_activation", "sh_coeffs", "alpha_before_
 
 
 class FlatGradients:
-    """Allocates one flat FP32 buffer and points every parameter's .grad at a slice of it."""
+    """One flat FP32 buffer holding every leaf gradient; the parameters' `.grad`s are views of it,
+    so the data-parallel exchange is a single all-reduce with no packing copy.
+
+    attach(renderer) additionally makes the renderer's backward kernels write / accumulate straight
+    into those views (`renderer.grad_buffers`); such steps must use `backward_into()` (which calls
+    torch.autograd.grad) instead of `loss.backward()`, because autograd's own accumulation would add
+    the buffer to itself."""
 
     def __init__(self, module):
+        self.names = list(_PARAMS)
         self.params = [getattr(module, n) for n in _PARAMS]
         total = sum(p.numel() for p in self.params)
         self.flat = torch.zeros(total, dtype=torch.float32, device=self.params[0].device)
@@ -29,11 +36,29 @@ class FlatGradients:
             p.grad = v
             self.views.append(v)
             off += p.numel()
+        self.module = None
+
+    def attach(self, renderer):
+        renderer.grad_buffers = dict(zip(self.names, self.views))
+        self.module = renderer
+        return self
+
+    def detach(self):
+        if self.module is not None:
+            self.module.grad_buffers = None
+            self.module = None
 
     def zero(self):
         self.flat.zero_()
         for p, v in zip(self.params, self.views):
             p.grad = v  # optimisers / zero_grad(set_to_none) may have dropped the alias
+
+    def backward_into(self, loss):
+        """Run backward for `loss`; the kernels add the leaf gradients into the flat buffer."""
+        if self.module is None:
+            loss.backward()  # plain autograd accumulation into the aliased .grad views
+        else:
+            torch.autograd.grad(loss, self.params)
 
     def all_reduce(self, group=None, average=False):
         if dist.is_initialized() and dist.get_world_size(group) > 1:
@@ -61,7 +86,7 @@ def view_sharded_step(renderer, flat, c2ws, camera_info, targets, loss_fn=None, 
     for i in shard_views(len(c2ws), rank, world):
         out = renderer(c2ws[i], camera_info)
         loss = loss_fn(out, targets[i])
-        loss.backward()  # accumulates into the aliased flat buffer
+        flat.backward_into(loss)  # accumulates into the flat buffer
         total = loss.detach() if total is None else total + loss.detach()
     flat.all_reduce(group)
     sync_adc(renderer, group)

@@ -171,7 +171,8 @@ int gs3d_composite_sh_backward(uint32_t M, const float *records, const float *sh
  * of sh_renderer.py:602-623: when adc_mode != 0,
  * grad_mean_acc[i] = max(., ||grad_mean2d_i||) (adc_mode 1, split_reduction "max") or
  * += ||grad_mean2d_i|| (adc_mode 2, "mean") for split_type "2d_mean_grad".
- * Leaf gradients are OVERWRITTEN. */
+ * Leaf gradients are OVERWRITTEN, or -- accumulate != 0, used when several views share one
+ * gradient buffer (view-sharded training) -- ADDED for the Gaussians with mask != 0. */
 int gs3d_project_backward_fused(uint32_t N, const uint8_t *mask, const float *mean,
                                 const float *qvec, const float *svec_param,
                                 const float *alpha_param, int svec_act, int alpha_act,
@@ -179,7 +180,7 @@ int gs3d_project_backward_fused(uint32_t N, const uint8_t *mask, const float *me
                                 const float *grad_cov2d, const float *grad_alpha,
                                 float *grad_mean, float *grad_qvec, float *grad_svec_param,
                                 float *grad_alpha_param, float *grad_mean_acc, int adc_mode,
-                                void *stream);
+                                int accumulate, void *stream);
 
 #ifdef __cplusplus
 }

@@ -1,0 +1,101 @@
+#!/usr/bin/env python
+"""Side benchmarks for the other BASELINE configs (evidence for SURVEY.md 8d rows; bench.py stays the
+contract bench for cfg 2 / cfg 4):
+
+  cfg3  500 k Gaussians, C=3, 1008x756: FULL training step = forward + L2 loss + backward +
+        ADC position-grad accumulation (fused into the projection-backward kernel) + cnt + Adam.
+  cfg5  6 M Gaussians, C=4, 3840x2160 forward; on N ranks (torchrun) tile rows are sharded.
+
+  python tools/bench_configs.py cfg3
+  python -m torch.distributed.run --nproc-per-node 8 --master-addr 127.0.0.1 tools/bench_configs.py cfg5
+"""
+import json
+import os
+import sys
+from pathlib import Path
+
+import torch
+import torch.distributed as dist
+
+sys.path.insert(0, str(Path(__file__).resolve().parent.parent))
+from gaussian_splatting_3d_b200 import parallel as P  # noqa: E402
+from gaussian_splatting_3d_b200 import synthetic as S  # noqa: E402
+
+
+def timed(fn, k, world, dev):
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(k):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / k
+    if world > 1:
+        t = torch.tensor([ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    return ms
+
+
+def main():
+    which = sys.argv[1] if len(sys.argv) > 1 else "cfg3"
+    steps = int(sys.argv[2]) if len(sys.argv) > 2 else 20
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    dev = torch.device(f"cuda:{local}")
+    torch.cuda.set_device(dev)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    cam = S.make_camera(which)
+    sc = S.make_scene(which, seed=0)
+    C = sc["C"]
+    r = S.renderer_from_scene(sc, S.make_cfg(device=str(dev), sh_order=C))
+    c2w = sc["c2w"].to(dev)
+    out = {"config": which, "N": r.N, "C": C, "image": [cam.w, cam.h], "n_gpus": world, "steps": steps}
+    if which == "cfg3":
+        r.train()
+        r.fuse_adc = True
+        tgt = S.make_target(cam, 0).to(dev)
+        opt = r.get_optimizer(0)
+
+        def step():
+            o = r(c2w, cam)
+            loss = ((o - tgt) ** 2).mean()
+            opt.zero_grad(set_to_none=True)
+            loss.backward()
+            r.update_grads()
+            opt.step()
+
+        for _ in range(3):
+            step()
+        ms = timed(step, steps, world, dev)
+        out.update({"metric": "full training steps/s (fwd + L2 + bwd + ADC accumulation + Adam)",
+                    "ms_per_step": ms, "value": 1000.0 / ms, "n_dub": r.total_dub_gaussians})
+    else:
+        r.eval()
+
+        def frame():
+            return P.tile_sharded_render(r, c2w, cam)
+
+        for _ in range(3):
+            frame()
+        ms = timed(frame, steps, world, dev)
+        out.update({"metric": "forward FPS, tile rows sharded over ranks (all_gather of bands included)",
+                    "ms_per_frame": ms, "value": 1000.0 / ms})
+        if world == 1:
+            out["n_dub"] = None
+            with torch.no_grad():
+                r(c2w, cam)
+            out["n_dub"] = r.total_dub_gaussians
+    if rank == 0:
+        print(json.dumps(out), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
