@@ -37,6 +37,9 @@ def parse():
     ap.add_argument("--n-gaussians", type=int, default=None, help="override N (debugging)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-exact", action="store_true", help="disable exact skip decisions")
+    ap.add_argument("--dp-mode", default="fused", choices=["fused", "allreduce"],
+                    help="N>1: 'fused' = SH gradients reduced into all ranks by the backward kernel over "
+                         "NVLink/NVSwitch + small all-reduce; 'allreduce' = one dense NCCL all-reduce")
     return ap.parse_args()
 
 
@@ -184,7 +187,7 @@ def run_ours(args, rank, local_rank, world):
         # summed over the ranks with a single NCCL all-reduce per step
         from gaussian_splatting_3d_b200 import parallel as P
 
-        flat = P.FlatGradients(r).attach(r)
+        flat = P.FlatGradients(r, fused=(args.dp_mode == "fused")).attach(r)
 
     def step(e2e):
         if e2e:
@@ -197,7 +200,7 @@ def run_ours(args, rank, local_rank, world):
         if world > 1:
             flat.zero()
             flat.backward_into(loss)
-            flat.all_reduce()
+            flat.exchange()
         else:
             for p in params:
                 p.grad = None
@@ -302,6 +305,9 @@ def run_ours(args, rank, local_rank, world):
         "config": {"workload": f"{name}: {N} Gaussians, SH degree {C - 1} (C={C}), {cam.w}x{cam.h}, "
                                f"1 view/step/GPU, fwd + L2 loss + bwd", "n_dub": n_dub,
                    "views_per_step": world, "parallelism": f"dp{world}" if world > 1 else "single",
+                   "dp_exchange": (None if world == 1 else
+                                   ("in-kernel multimem/peer reduction of SH grads + 132 MB all-reduce"
+                                    if flat.fused else "dense 708 MB NCCL all-reduce")),
                    "l2_policy": "inputs larger than L2 (parameters 708 MB, duplicates 132 MB vs 126 MB L2)",
                    "exact_decisions": not args.no_exact},
         "fwd_fps": world * 1000.0 * args.steps / ms_fwd,

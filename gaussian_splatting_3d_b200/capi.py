@@ -53,6 +53,9 @@ SIGNATURES = {
     "gs3d_composite_sh_backward": (_i, [_u32, _P, _P, _u32, _u32, _P, _P, _P, _P, _P, _P, _P, _P,
                                         _u32, _u32, _P, _P, _P, _u32, _u32, _u32, _f, _f, _u32, _u32,
                                         _u32, _f, _i, _P]),
+    "gs3d_composite_sh_backward_peers": (_i, [_u32, _P, _P, _u32, _u32, _P, _P, _P, _P, _P, _P, _P, _P,
+                                              _u32, _u32, _P, _P, _P, _u32, _u32, _u32, _f, _f, _u32, _u32,
+                                              _u32, _f, _i, _P, _i, _P, _P]),
     "gs3d_project_backward_fused": (_i, [_u32, _P, _P, _P, _P, _P, _i, _i, _P, _i, _P, _P, _P, _P, _P,
                                          _P, _P, _P, _i, _i, _P]),
 }

@@ -53,6 +53,12 @@ struct CompositeParams {
   uint32_t gsh_sg, gsh_sc;
   int sh_vec;   // SH rows are 16-byte addressable (staging)
   int gsh_vec;  // grad SH rows are 16-byte addressable (vector reductions)
+  // fused gradient exchange (view-sharded training): the SH gradient rows are reduced straight into
+  // every rank's buffer -- through one multimem.red on an NVSwitch multicast address, or peer by peer
+  // over NVLink -- instead of locally followed by a dense all-reduce.  n_peers == 0: local only.
+  float *g_sh_peer[8];
+  int n_peers;
+  float *g_sh_mc;
 };
 
 // ---------------------------------------------------------------- small device helpers
@@ -78,6 +84,11 @@ __device__ __forceinline__ float ex2_approx(float x) {
 __device__ __forceinline__ void red_add_v4(float *addr, float4 v) {
   asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};\n" ::"l"(addr), "f"(v.x), "f"(v.y),
                "f"(v.z), "f"(v.w)
+               : "memory");
+}
+__device__ __forceinline__ void multimem_red_add_v4(float *addr, float4 v) {
+  asm volatile("multimem.red.relaxed.sys.global.add.v4.f32 [%0], {%1, %2, %3, %4};\n" ::"l"(addr), "f"(v.x),
+               "f"(v.y), "f"(v.z), "f"(v.w)
                : "memory");
 }
 __device__ __forceinline__ float rcp_approx(float x) {
@@ -548,7 +559,14 @@ composite_bwd_kernel(const CompositeParams p) {
       const int r0 = 4 * q;
       if (CC % 4 == 0 && p.gsh_vec && r0 + 3 < SHF) {
         const int c = r0 / CC, k = r0 - c * CC;
-        red_add_v4(p.g_sh + g * p.gsh_sg + c * p.gsh_sc + k, s);
+        const size_t off = g * p.gsh_sg + c * p.gsh_sc + k;
+        if (p.g_sh_mc) {
+          multimem_red_add_v4(p.g_sh_mc + off, s);  // one instruction, the switch adds it on every GPU
+        } else if (p.n_peers > 0) {
+          for (int r = 0; r < p.n_peers; ++r) red_add_v4(p.g_sh_peer[r] + off, s);
+        } else {
+          red_add_v4(p.g_sh + off, s);
+        }
       } else {
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
@@ -557,7 +575,12 @@ composite_bwd_kernel(const CompositeParams p) {
           if (val == 0.f) continue;
           if (r < SHF) {
             const int c = r / CC, k = r - c * CC;
-            atomicAdd(p.g_sh + g * p.gsh_sg + c * p.gsh_sc + k, val);
+            const size_t off = g * p.gsh_sg + c * p.gsh_sc + k;
+            if (p.n_peers > 0) {
+              for (int q2 = 0; q2 < p.n_peers; ++q2) atomicAdd(p.g_sh_peer[q2] + off, val);
+            } else {
+              atomicAdd(p.g_sh + off, val);
+            }
           } else {
             const int v = r - SHF;
             if (v == 0) atomicAdd(p.g_mean + 2 * g, val);
@@ -673,7 +696,7 @@ int gs3d_composite_sh_forward(uint32_t M, const float *records, const float *sh_
   }
 }
 
-int gs3d_composite_sh_backward(uint32_t M, const float *records, const float *sh_coeffs,
+int gs3d_composite_sh_backward_peers(uint32_t M, const float *records, const float *sh_coeffs,
                                uint32_t sh_stride_g, uint32_t sh_stride_c, const int32_t *start,
                                const int32_t *end, const int32_t *gaussian_ids, const float *out,
                                const float *grad_out, float *grad_mean2d, float *grad_cov2d,
@@ -681,7 +704,9 @@ int gs3d_composite_sh_backward(uint32_t M, const float *records, const float *sh
                                float *grad_alpha, const float *topleft, const float *c2w,
                                uint32_t tile_size, uint32_t n_tiles_h, uint32_t n_tiles_w,
                                float pixel_size_x, float pixel_size_y, uint32_t H, uint32_t W,
-                               uint32_t C, float thresh, int exact_decisions, void *stream) {
+                               uint32_t C, float thresh, int exact_decisions,
+                               const uint64_t *peer_grad_sh_host, int n_peers,
+                               void *multicast_grad_sh, void *stream) {
   (void)M;
   GS3D_REQUIRE(tile_size == TILE, GS3D_EUNSUPPORTED,
                "compositing kernels support tile_size 16 only (got %u)", tile_size);
@@ -705,6 +730,15 @@ int gs3d_composite_sh_backward(uint32_t M, const float *records, const float *sh
   const uint32_t CC = C * C;
   p.sh_vec = (CC % 4 == 0) && (sh_stride_g % 4 == 0) && (sh_stride_c % 4 == 0) && aligned16(sh_coeffs);
   p.gsh_vec = (CC % 4 == 0) && (gsh_stride_g % 4 == 0) && (gsh_stride_c % 4 == 0) && aligned16(grad_sh);
+  GS3D_REQUIRE(n_peers >= 0 && n_peers <= 8, GS3D_EINVAL, "n_peers must be 0..8 (got %d)", n_peers);
+  GS3D_REQUIRE(n_peers == 0 || peer_grad_sh_host, GS3D_EINVAL, "peer pointer array is null");
+  p.n_peers = n_peers;
+  for (int r = 0; r < n_peers; ++r) {
+    p.g_sh_peer[r] = reinterpret_cast<float *>(static_cast<uintptr_t>(peer_grad_sh_host[r]));
+    GS3D_REQUIRE(p.g_sh_peer[r] && aligned16(p.g_sh_peer[r]), GS3D_EINVAL, "bad peer pointer %d", r);
+  }
+  // the multicast path needs vector reductions; otherwise fall back to the per-peer loop
+  p.g_sh_mc = (multicast_grad_sh && p.gsh_vec && n_peers > 0) ? static_cast<float *>(multicast_grad_sh) : nullptr;
   cudaStream_t st = as_stream(stream);
   switch (C) {
     case 1: return launch_bwd<1>(p, n_tiles, st);
@@ -712,6 +746,22 @@ int gs3d_composite_sh_backward(uint32_t M, const float *records, const float *sh
     case 3: return launch_bwd<3>(p, n_tiles, st);
     default: return launch_bwd<4>(p, n_tiles, st);
   }
+}
+
+int gs3d_composite_sh_backward(uint32_t M, const float *records, const float *sh_coeffs,
+                               uint32_t sh_stride_g, uint32_t sh_stride_c, const int32_t *start,
+                               const int32_t *end, const int32_t *gaussian_ids, const float *out,
+                               const float *grad_out, float *grad_mean2d, float *grad_cov2d,
+                               float *grad_sh, uint32_t gsh_stride_g, uint32_t gsh_stride_c,
+                               float *grad_alpha, const float *topleft, const float *c2w,
+                               uint32_t tile_size, uint32_t n_tiles_h, uint32_t n_tiles_w,
+                               float pixel_size_x, float pixel_size_y, uint32_t H, uint32_t W,
+                               uint32_t C, float thresh, int exact_decisions, void *stream) {
+  return gs3d_composite_sh_backward_peers(M, records, sh_coeffs, sh_stride_g, sh_stride_c, start, end,
+                                          gaussian_ids, out, grad_out, grad_mean2d, grad_cov2d, grad_sh,
+                                          gsh_stride_g, gsh_stride_c, grad_alpha, topleft, c2w, tile_size,
+                                          n_tiles_h, n_tiles_w, pixel_size_x, pixel_size_y, H, W, C,
+                                          thresh, exact_decisions, nullptr, 0, nullptr, stream);
 }
 
 }  // extern "C"

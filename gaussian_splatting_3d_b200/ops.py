@@ -211,7 +211,10 @@ def composite_sh_forward(records, sh, start, end, gaussian_ids, out, topleft, c2
 # ---------------------------------------------------------------- a8 / a11
 def composite_sh_backward(records, sh, start, end, gaussian_ids, out, grad_out, grad_mean, grad_cov,
                           grad_sh, grad_alpha, topleft, c2w, tile_size, n_tiles_h, n_tiles_w,
-                          pixel_size_x, pixel_size_y, H, W, C_, thresh, exact=True):
+                          pixel_size_x, pixel_size_y, H, W, C_, thresh, exact=True, peer_ptrs=None,
+                          multicast_ptr=None):
+    """peer_ptrs: device addresses of every rank's grad_sh buffer (this rank included) for the fused
+    gradient exchange; multicast_ptr: NVSwitch multicast address of the same buffers (optional)."""
     _chk(records, "records", _F32)
     for t, n in ((start, "start"), (end, "end"), (gaussian_ids, "gaussian_ids")):
         _chk(t, n, _I32)
@@ -221,12 +224,16 @@ def composite_sh_backward(records, sh, start, end, gaussian_ids, out, grad_out, 
         _chk(t, n, _F32)
     sg, sc = _sh_strides(sh, C_)
     gsg, gsc = _sh_strides(grad_sh, C_)
-    check(capi.lib.gs3d_composite_sh_backward(
+    n_peers = 0 if not peer_ptrs else len(peer_ptrs)
+    arr = (C.c_uint64 * max(n_peers, 1))(*([int(x) for x in peer_ptrs] if n_peers else [0]))
+    check(capi.lib.gs3d_composite_sh_backward_peers(
         records.size(0), ptr(records), ptr(sh), sg, sc, ptr(start), ptr(end), ptr(gaussian_ids),
         ptr(out), ptr(grad_out), ptr(grad_mean), ptr(grad_cov), ptr(grad_sh), gsg, gsc,
         ptr(grad_alpha), ptr(topleft), ptr(c2w), int(tile_size), int(n_tiles_h), int(n_tiles_w),
         float(pixel_size_x), float(pixel_size_y), int(H), int(W), int(C_), float(thresh),
-        1 if exact else 0, _stream(out)), "tile_based_vol_rendering_backward_sh")
+        1 if exact else 0, C.cast(arr, C.c_void_p), n_peers,
+        C.c_void_p(int(multicast_ptr)) if multicast_ptr else None, _stream(out)),
+        "tile_based_vol_rendering_backward_sh")
 
 
 # ---------------------------------------------------------------- a9 + a10

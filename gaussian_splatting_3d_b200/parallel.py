@@ -17,18 +17,37 @@ _PARAMS = ("mean", "qvec", "svec_before_activation", "sh_coeffs", "alpha_before_
 
 class FlatGradients:
     """One flat FP32 buffer holding every leaf gradient; the parameters' `.grad`s are views of it,
-    so the data-parallel exchange is a single all-reduce with no packing copy.
+    so the data-parallel exchange needs no packing copy.  Layout: [sh_coeffs | mean | qvec | svec |
+    alpha] -- the SH block (576 of 708 MB at C = 4) first, the small dense block after it.
 
-    attach(renderer) additionally makes the renderer's backward kernels write / accumulate straight
-    into those views (`renderer.grad_buffers`); such steps must use `backward_into()` (which calls
-    torch.autograd.grad) instead of `loss.backward()`, because autograd's own accumulation would add
-    the buffer to itself."""
+    attach(renderer) makes the renderer's backward kernels write / accumulate straight into those
+    views (`renderer.grad_buffers`); such steps must use `backward_into()` (torch.autograd.grad)
+    instead of `loss.backward()`, because autograd's own accumulation would add the buffer to itself.
 
-    def __init__(self, module):
-        self.names = list(_PARAMS)
-        self.params = [getattr(module, n) for n in _PARAMS]
+    fused=True (needs an initialised NCCL group): the buffer is allocated as torch symmetric memory,
+    every rank maps every other rank's buffer (and the NVSwitch multicast address when available),
+    and the compositing-backward kernel reduces its SH gradient rows into ALL ranks' buffers while it
+    runs (gs3d_composite_sh_backward_peers).  exchange() then only all-reduces the small dense block.
+    """
+
+    ORDER = ("sh_coeffs", "mean", "qvec", "svec_before_activation", "alpha_before_activation")
+
+    def __init__(self, module, fused=False, group=None, use_multicast=True):
+        self.names = list(self.ORDER)
+        self.params = [getattr(module, n) for n in self.names]
         total = sum(p.numel() for p in self.params)
-        self.flat = torch.zeros(total, dtype=torch.float32, device=self.params[0].device)
+        dev = self.params[0].device
+        self.group = group
+        self.fused = bool(fused) and dist.is_initialized() and dist.get_world_size(group) > 1
+        self.handle = None
+        if self.fused:
+            import torch.distributed._symmetric_memory as symm_mem
+
+            self.flat = symm_mem.empty(total, dtype=torch.float32, device=dev)
+            self.handle = symm_mem.rendezvous(self.flat, group if group is not None else dist.group.WORLD)
+        else:
+            self.flat = torch.empty(total, dtype=torch.float32, device=dev)
+        self.flat.zero_()
         self.views = []
         off = 0
         for p in self.params:
@@ -36,10 +55,22 @@ class FlatGradients:
             p.grad = v
             self.views.append(v)
             off += p.numel()
+        self.n_sh = self.params[0].numel()
+        self.peer_ptrs = None
+        self.multicast_ptr = None
+        if self.fused:
+            # the SH block starts at offset 0 of the symmetric buffer on every rank
+            self.peer_ptrs = [int(p) for p in self.handle.buffer_ptrs]
+            mc = int(self.handle.multicast_ptr) if use_multicast else 0
+            self.multicast_ptr = mc if mc else None
         self.module = None
 
     def attach(self, renderer):
-        renderer.grad_buffers = dict(zip(self.names, self.views))
+        bufs = dict(zip(self.names, self.views))
+        if self.fused:
+            bufs["sh_peer_ptrs"] = self.peer_ptrs
+            bufs["sh_multicast_ptr"] = self.multicast_ptr
+        renderer.grad_buffers = bufs
         self.module = renderer
         return self
 
@@ -48,10 +79,18 @@ class FlatGradients:
             self.module.grad_buffers = None
             self.module = None
 
+    def _barrier(self):
+        if self.handle is not None:
+            self.handle.barrier(channel=0)
+        elif dist.is_initialized():
+            dist.barrier(group=self.group)
+
     def zero(self):
         self.flat.zero_()
         for p, v in zip(self.params, self.views):
             p.grad = v  # optimisers / zero_grad(set_to_none) may have dropped the alias
+        if self.fused:
+            self._barrier()  # nobody may add into a buffer that is not zeroed yet
 
     def backward_into(self, loss):
         """Run backward for `loss`; the kernels add the leaf gradients into the flat buffer."""
@@ -60,12 +99,21 @@ class FlatGradients:
         else:
             torch.autograd.grad(loss, self.params)
 
-    def all_reduce(self, group=None, average=False):
-        if dist.is_initialized() and dist.get_world_size(group) > 1:
-            dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=group)
-            if average:
-                self.flat.div_(dist.get_world_size(group))
+    def exchange(self, average=False):
+        """Make every rank's buffer hold the sum over ranks."""
+        if not (dist.is_initialized() and dist.get_world_size(self.group) > 1):
+            return self.flat
+        if self.fused and self.module is not None:
+            self._barrier()  # every rank's in-kernel reductions into this buffer have landed
+            dist.all_reduce(self.flat[self.n_sh:], op=dist.ReduceOp.SUM, group=self.group)
+        else:
+            dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=self.group)
+        if average:
+            self.flat.div_(dist.get_world_size(self.group))
         return self.flat
+
+    def all_reduce(self, group=None, average=False):
+        return self.exchange(average=average)
 
 
 def shard_views(n_views, rank, world):
@@ -88,7 +136,7 @@ def view_sharded_step(renderer, flat, c2ws, camera_info, targets, loss_fn=None, 
         loss = loss_fn(out, targets[i])
         flat.backward_into(loss)  # accumulates into the flat buffer
         total = loss.detach() if total is None else total + loss.detach()
-    flat.all_reduce(group)
+    flat.exchange()
     sync_adc(renderer, group)
     return total
 

@@ -165,6 +165,27 @@ int gs3d_composite_sh_backward(uint32_t M, const float *records, const float *sh
                                float pixel_size_x, float pixel_size_y, uint32_t H, uint32_t W,
                                uint32_t C, float thresh, int exact_decisions, void *stream);
 
+/* Same kernel with the FUSED GRADIENT EXCHANGE of view-sharded training (new capability; the
+ * reference has no multi-GPU code): the SH-coefficient gradient rows -- 576 of the 708 MB of leaf
+ * gradients at C = 4, and sparse in practice -- are reduced by the compositing-backward kernel itself
+ * into EVERY rank's gradient buffer while it computes: with one `multimem.red.add.v4.f32` per row
+ * chunk on an NVSwitch multicast address (multicast_grad_sh != NULL) or with one red.global.add per
+ * peer over NVLink (peer_grad_sh_host[0..n_peers): device addresses of each rank's grad_sh, this
+ * rank included).  All buffers must be zeroed and a cross-rank barrier passed before the launch;
+ * after a second barrier each buffer holds the sum over ranks.  n_peers == 0: identical to
+ * gs3d_composite_sh_backward. */
+int gs3d_composite_sh_backward_peers(uint32_t M, const float *records, const float *sh_coeffs,
+                                     uint32_t sh_stride_g, uint32_t sh_stride_c, const int32_t *start,
+                                     const int32_t *end, const int32_t *gaussian_ids, const float *out,
+                                     const float *grad_out, float *grad_mean2d, float *grad_cov2d,
+                                     float *grad_sh, uint32_t gsh_stride_g, uint32_t gsh_stride_c,
+                                     float *grad_alpha, const float *topleft, const float *c2w,
+                                     uint32_t tile_size, uint32_t n_tiles_h, uint32_t n_tiles_w,
+                                     float pixel_size_x, float pixel_size_y, uint32_t H, uint32_t W,
+                                     uint32_t C, float thresh, int exact_decisions,
+                                     const uint64_t *peer_grad_sh_host, int n_peers,
+                                     void *multicast_grad_sh, void *stream);
+
 /* ---- a9 + a10 fused: chain rule from (grad_mean2d, grad_cov2d, grad_alpha) to the leaf
  * parameters through projection (Q6) and the activations (sh_renderer.py:318-324), for the
  * Gaussians with mask != 0 (others get zero gradient; mask NULL = all), plus the ADC accumulator

@@ -69,6 +69,7 @@ def _worker(rank, world, port, q):
         c2ws.append(torch.tensor([[math.cos(a), 0, math.sin(a), 0], [0, 1, 0, 0], [-math.sin(a), 0, math.cos(a), 0]],
                                  dtype=torch.float32, device=dev))
     targets = [S.make_target(cam, i).to(dev) for i in range(4)]
+    r._reset_adc_buffers()  # the renders above already counted one view
     flat = P.FlatGradients(r)
     P.view_sharded_step(r, flat, c2ws, cam, targets)
     sharded = flat.flat.clone()
@@ -102,3 +103,63 @@ def test_two_gpu_tile_sharded_render_and_view_sharded_training():
         assert ok_render, f"rank {rank}: tile-sharded frame differs from the single-GPU frame"
         assert rel < 1e-4, f"rank {rank}: view-sharded gradient sum differs (rel {rel:.2e})"
         assert cnt_ok
+
+
+def _worker_fused(rank, world, port, q, use_multicast):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dev = f"cuda:{rank}"
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device(dev))
+    import math
+
+    from gaussian_splatting_3d_b200 import parallel as P
+
+    r, sc, cam = _renderer(dev, name="cfg2", n=80_000, C=4)
+    r.train()
+    c2ws = []
+    for i in range(4):
+        a = math.radians(3.0 * (i - 1.5))
+        c2ws.append(torch.tensor([[math.cos(a), 0, math.sin(a), 0], [0, 1, 0, 0], [-math.sin(a), 0, math.cos(a), 0]],
+                                 dtype=torch.float32, device=dev))
+    targets = [S.make_target(cam, i).to(dev) for i in range(4)]
+    flat = P.FlatGradients(r, fused=True, use_multicast=use_multicast).attach(r)
+    info = (flat.fused, flat.multicast_ptr is not None, len(flat.peer_ptrs or []))
+    for _ in range(2):  # twice: the buffers must be re-zeroed and re-synchronised correctly
+        P.view_sharded_step(r, flat, c2ws, cam, targets)
+    fused_sum = flat.flat.clone()
+    # serial reference on this rank: all four views with plain autograd accumulation
+    r2, _, _ = _renderer(dev, name="cfg2", n=80_000, C=4)
+    r2.train()
+    flat2 = P.FlatGradients(r2)
+    flat2.zero()
+    for i in range(4):
+        ((r2(c2ws[i], cam) - targets[i]) ** 2).mean().backward()
+    n_sh = flat.n_sh
+    rel_sh = float((fused_sum[:n_sh] - flat2.flat[:n_sh]).norm() / flat2.flat[:n_sh].norm())
+    rel_rest = float((fused_sum[n_sh:] - flat2.flat[n_sh:]).norm() / flat2.flat[n_sh:].norm())
+    q.put((rank, info, rel_sh, rel_rest))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
+@pytest.mark.parametrize("use_multicast", [False, True])
+def test_two_gpu_fused_gradient_exchange(use_multicast):
+    """SH gradients reduced into both ranks' buffers by the backward kernel itself (peer stores or
+    NVSwitch multimem) + small all-reduce == serial sum over the four views."""
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29700 + (os.getpid() % 2000) + (7 if use_multicast else 0)
+    procs = [ctx.Process(target=_worker_fused, args=(r, 2, port, q, use_multicast)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=300) for _ in range(2)]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for rank, info, rel_sh, rel_rest in res:
+        print(f"[fused dp rank {rank}] fused={info[0]} multicast={info[1]} peers={info[2]} "
+              f"rel_sh={rel_sh:.2e} rel_rest={rel_rest:.2e}")
+        assert info[0] and info[2] == 2
+        assert rel_sh < 1e-4 and rel_rest < 1e-4

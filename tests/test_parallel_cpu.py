@@ -101,7 +101,8 @@ def test_view_sharded_gradient_allreduce_gloo_world2():
     ps = [torch.randn(n, 3, generator=g), torch.randn(n, 4, generator=g), torch.randn(n, 3, generator=g),
           torch.randn(n, 3, 4, generator=g), torch.randn(n, generator=g)]
     scale = sum(2.0 * (v + 1) ** 2 for v in range(8))
-    want = torch.cat([(p * scale).reshape(-1) for p in ps])
+    # flat layout: [sh_coeffs | mean | qvec | svec | alpha]
+    want = torch.cat([(p * scale).reshape(-1) for p in (ps[3], ps[0], ps[1], ps[2], ps[4])])
     assert torch.allclose(f0, want, rtol=1e-5, atol=1e-5)
     assert torch.equal(gm0, gm1) and float(gm0[0]) == float(sum(range(1, 9)))
     assert torch.equal(c0, c1) and int(c0[0]) == 8
