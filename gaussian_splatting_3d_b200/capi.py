@@ -10,7 +10,8 @@ import os
 from pathlib import Path
 
 _PKG = Path(__file__).resolve().parent
-LIB_PATH = _PKG / "libgs3d_b200.so"
+# GS3D_LIB: developer override used by tools/ablate.sh to time experimental builds of the same ABI
+LIB_PATH = Path(os.environ["GS3D_LIB"]) if os.environ.get("GS3D_LIB") else _PKG / "libgs3d_b200.so"
 
 
 class Camera(C.Structure):

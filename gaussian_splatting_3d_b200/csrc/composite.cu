@@ -100,6 +100,28 @@ __device__ __forceinline__ float rcp_approx(float x) {
 __device__ __forceinline__ float fast_sigmoid(float s) {
   return rcp_approx(1.0f + ex2_approx(s * -1.4426950408889634f));
 }
+// Packed FP32 pairs (Blackwell FFMA2: one issue slot, two FMAs).  The compositing kernels are
+// issue-bound (ncu: 70-80 % issue-slot utilisation, FMA pipe < 50 %), so the SH dot products and the
+// backward's per-warp GEMV run on fma.rn.f32x2 with operands that come out of LDS.128 as register pairs.
+typedef unsigned long long f32x2;
+__device__ __forceinline__ f32x2 pack2(float lo, float hi) {
+  f32x2 r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ float sum2(f32x2 v) {
+  float lo, hi;
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+  return lo + hi;
+}
+__device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) {
+  f32x2 r;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+  return r;
+}
+__device__ __forceinline__ void lds128_2(uint32_t a, f32x2 &lo, f32x2 &hi) {
+  asm volatile("ld.shared.v2.b64 {%0, %1}, [%2];" : "=l"(lo), "=l"(hi) : "r"(a));
+}
 // 32-bit shared-window addresses kept in registers: the hot loops address staging buffers with
 // plain adds instead of re-deriving generic pointers every iteration.
 __device__ __forceinline__ uint32_t smem_u32(const void *p) {
@@ -224,31 +246,77 @@ __device__ __forceinline__ void stage_batch(const CompositeParams &p, const int 
   }
 }
 
+// Per-pixel SH basis held in registers: packed pairs when C*C is a multiple of 4 (C = 2, 4),
+// scalars otherwise (C = 1, 3).
 template <int CC>
-__device__ __forceinline__ void sh_colour(uint32_t h_addr, const float *Y, float coeff, float *y) {
+struct Basis {
+  static constexpr bool PACKED = (CC % 4 == 0);
+  static constexpr int NP = PACKED ? CC / 2 : 1;
+  static constexpr int NS = PACKED ? 1 : CC;
+  f32x2 p[NP];
+  float s[NS];
+  __device__ __forceinline__ void set(const float *Y) {
+    if constexpr (PACKED) {
 #pragma unroll
-  for (int c = 0; c < 3; ++c) {
-    float s = 0.0f;
-    if constexpr (CC % 4 == 0) {
-#pragma unroll
-      for (int k = 0; k < CC / 4; ++k) {
-        const float4 v = lds128(h_addr + 4 * (c * CC + 4 * k));
-        s = fmaf(v.x, Y[4 * k], s);
-        s = fmaf(v.y, Y[4 * k + 1], s);
-        s = fmaf(v.z, Y[4 * k + 2], s);
-        s = fmaf(v.w, Y[4 * k + 3], s);
-      }
+      for (int k = 0; k < CC / 2; ++k) p[k] = pack2(Y[2 * k], Y[2 * k + 1]);
     } else {
 #pragma unroll
-      for (int k = 0; k < CC; ++k) s = fmaf(lds32(h_addr + 4 * (c * CC + k)), Y[k], s);
+      for (int k = 0; k < CC; ++k) s[k] = Y[k];
     }
+  }
+};
+
+#ifndef GS3D_ABLATE
+#define GS3D_ABLATE 0  // experiment switches (tools/ablate.sh); 0 in every shipped build
+#endif
+template <int CC>
+__device__ __forceinline__ void sh_colour(uint32_t h_addr, const Basis<CC> &Y, float *y) {
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    float s;
+    if constexpr (Basis<CC>::PACKED) {
+      f32x2 acc = 0ull;
+#if GS3D_ABLATE & 2   // no SH row loads: one LDS.128 per channel instead of CC/4
+      f32x2 lo, hi;
+      lds128_2(h_addr + 4 * (c * CC), lo, hi);
+#endif
+#pragma unroll
+      for (int k = 0; k < CC / 4; ++k) {
+#if !(GS3D_ABLATE & 2)
+        f32x2 lo, hi;
+        lds128_2(h_addr + 4 * (c * CC + 4 * k), lo, hi);
+#endif
+#if GS3D_ABLATE & 4   // a quarter of the FMAs
+        if (k > 0) continue;
+#endif
+        acc = fma2(lo, Y.p[2 * k], acc);
+        acc = fma2(hi, Y.p[2 * k + 1], acc);
+      }
+      s = sum2(acc);
+    } else {
+      s = 0.0f;
+#pragma unroll
+      for (int k = 0; k < CC; ++k) s = fmaf(lds32(h_addr + 4 * (c * CC + k)), Y.s[k], s);
+    }
+#if GS3D_ABLATE & 1     // no MUFU in the sigmoid
+    float v = fminf(fmaxf(fmaf(s, 0.05f, 0.5f), 0.0f), 1.0f);
+#else
     float v = fast_sigmoid(s);
-    if (isnan(v * coeff)) v = 0.0f;  // vol_render_sh.h:151-159
+#endif
+    // vol_render_sh.h:151-159 zeroes a colour whose product with the (finite, NaN-guarded) weight is
+    // NaN; the sigmoid is in [0,1] or NaN, so that is exactly "v is NaN"
+    if (isnan(v)) v = 0.0f;
     y[c] = v;
   }
 }
 
 // ---------------------------------------------------------------- forward
+//
+// Pipeline (one barrier per batch): the ids of batch b+2 are fetched into a register and published
+// to a three-deep id ring while batch b+1 is in flight (cp.async) and batch b is composited.  The
+// single __syncthreads_and per batch (i) makes batch b's staged rows visible, (ii) releases the
+// buffer batch b-1 used, (iii) publishes the id ring slot and (iv) carries the "every pixel of the
+// tile is saturated" vote that ends the tile early.
 
 template <int C, int B, bool EXACT>
 __global__ void __launch_bounds__(NTHREADS)
@@ -258,7 +326,7 @@ composite_fwd_kernel(const CompositeParams p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   float4 *s_rec = reinterpret_cast<float4 *>(smem_raw);        // [2][B][3]
   float *s_sh = reinterpret_cast<float *>(s_rec + 2 * B * 3);  // [2][B][SHF]
-  int *s_ids = reinterpret_cast<int *>(s_sh + 2 * B * SHF);    // [2][B]
+  int *s_ids = reinterpret_cast<int *>(s_sh + 2 * B * SHF);    // [3][B]
 
   const int tile_id = blockIdx.x;
   const int tile_y = tile_id / p.ntw, tile_x = tile_id - tile_y * p.ntw;
@@ -286,8 +354,12 @@ composite_fwd_kernel(const CompositeParams p) {
 
   // pixel corner in camera-plane units (quirk Q4), same expression as vol_render_sh.h:213-214
   const float px = p.topleft[0] + gx * p.psx, py = p.topleft[1] + gy * p.psy;
-  float Y[CC];
-  pixel_basis<C>(p.c2w, px, py, Y);
+  Basis<CC> Y;
+  {
+    float Yf[CC];
+    pixel_basis<C>(p.c2w, px, py, Yf);
+    Y.set(Yf);
+  }
 
   float T = 1.0f, o0 = 0.0f, o1 = 0.0f, o2 = 0.0f;
   int last = 0;
@@ -295,50 +367,52 @@ composite_fwd_kernel(const CompositeParams p) {
   bool alive = inside && !(1.0f < thresh);  // the reference tests T (initially 1) before each Gaussian
   const int32_t *ids = p.ids + first;
   const int n_batches = (n_this + B - 1) / B;
+  const bool id_lane = threadIdx.x < B;
 
-  int my_id = (threadIdx.x < B && threadIdx.x < n_this) ? ids[threadIdx.x] : 0;
-  for (int b = 0; b <= n_batches; ++b) {
-    if (b < n_batches) {
-      const int buf = b & 1;
-      const int nb = min(B, n_this - b * B);
-      if (threadIdx.x < B) s_ids[buf * B + threadIdx.x] = my_id;
-      __syncthreads();
-      int nxt = (b + 1) * B + threadIdx.x;
-      my_id = (threadIdx.x < B && nxt < n_this) ? ids[nxt] : 0;
-      stage_batch<CC, B>(p, s_ids + buf * B, nb, s_rec + buf * B * 3, s_sh + buf * B * SHF);
+  // prologue: ids of batch 0 -> ring slot 0, batch 0 in flight, ids of batch 1 -> ring slot 1
+  if (id_lane) s_ids[threadIdx.x] = threadIdx.x < n_this ? ids[threadIdx.x] : 0;
+  int my_id = (id_lane && B + threadIdx.x < n_this) ? ids[B + threadIdx.x] : 0;
+  __syncthreads();
+  stage_batch<CC, B>(p, s_ids, min(B, n_this), s_rec, s_sh);
+  cp_async_commit();
+  if (id_lane) s_ids[B + threadIdx.x] = my_id;
+  my_id = (id_lane && 2 * B + threadIdx.x < n_this) ? ids[2 * B + threadIdx.x] : 0;
+
+  for (int cb = 0; cb < n_batches; ++cb) {
+    cp_async_wait<0>();
+    if (__syncthreads_and(!alive)) break;  // all pixels of the tile finished -> stop staging
+    const int buf = cb & 1;
+    if (cb + 1 < n_batches) {
+      const int nbuf = buf ^ 1;
+      stage_batch<CC, B>(p, s_ids + ((cb + 1) % 3) * B, min(B, n_this - (cb + 1) * B), s_rec + nbuf * B * 3,
+                         s_sh + nbuf * B * SHF);
+      cp_async_commit();
+      if (id_lane) s_ids[((cb + 2) % 3) * B + threadIdx.x] = my_id;
+      const int nxt = (cb + 3) * B + threadIdx.x;
+      my_id = (id_lane && nxt < n_this) ? ids[nxt] : 0;
     }
-    cp_async_commit();
-    if (b == 0) continue;
-    cp_async_wait<1>();
-    __syncthreads();
-    {
-      const int cb = b - 1;
-      const int buf = cb & 1;
-      const int nb = min(B, n_this - cb * B);
-      uint32_t rec_a = smem_u32(s_rec + buf * B * 3);
-      uint32_t sh_a = smem_u32(s_sh + buf * B * SHF);
-      for (int j = 0; j < nb; ++j, rec_a += 48, sh_a += 4 * SHF) {
-        if ((j & 7) == 0 && !__any_sync(0xffffffffu, alive)) break;
-        if (!alive) continue;
-        const float4 r0 = lds128(rec_a), r1 = lds128(rec_a + 16);
-        float G;
-        if (!eval_pair<EXACT>(px, py, r0, r1, rec_a + 32, G)) continue;
-        const float a = r0.z;
-        float coeff = (a * T) * G;
-        if (isnan(coeff)) coeff = 0.0f;
-        float y[3];
-        sh_colour<CC>(sh_a, Y, coeff, y);
-        o0 = fmaf(coeff, y[0], o0);
-        o1 = fmaf(coeff, y[1], o1);
-        o2 = fmaf(coeff, y[2], o2);
-        T *= (1 - a * G);
-        last = cb * B + j + 1;
-        // vol_render_sh.h:121-123 tests T before each Gaussian; T only changes here
-        if (T < thresh) alive = false;
-      }
+    const int nb = min(B, n_this - cb * B);
+    uint32_t rec_a = smem_u32(s_rec + buf * B * 3);
+    uint32_t sh_a = smem_u32(s_sh + buf * B * SHF);
+    for (int j = 0; j < nb; ++j, rec_a += 48, sh_a += 4 * SHF) {
+      if ((j & 7) == 0 && !__any_sync(0xffffffffu, alive)) break;
+      if (!alive) continue;
+      const float4 r0 = lds128(rec_a), r1 = lds128(rec_a + 16);
+      float G;
+      if (!eval_pair<EXACT>(px, py, r0, r1, rec_a + 32, G)) continue;
+      const float a = r0.z;
+      float coeff = (a * T) * G;
+      if (isnan(coeff)) coeff = 0.0f;
+      float y[3];
+      sh_colour<CC>(sh_a, Y, y);
+      o0 = fmaf(coeff, y[0], o0);
+      o1 = fmaf(coeff, y[1], o1);
+      o2 = fmaf(coeff, y[2], o2);
+      T *= (1 - a * G);
+      last = cb * B + j + 1;
+      // vol_render_sh.h:121-123 tests T before each Gaussian; T only changes here
+      if (T < thresh) alive = false;
     }
-    // all pixels of the tile finished -> stop staging (uniform decision, doubles as barrier)
-    if (__syncthreads_and(!alive)) break;
   }
   cp_async_wait<0>();
   if (!inside) return;
@@ -356,6 +430,70 @@ composite_fwd_kernel(const CompositeParams p) {
 
 // ---------------------------------------------------------------- backward
 
+constexpr int WROW = 36;  // floats per row of the per-warp exchange tile (32 pixels + 4 pad: the
+                          // scalar-sum LDS.128 of rows v and v+1 then fall on different banks)
+
+// Sum the 8 warp-private accumulator rows of one batch, reduce into global memory, re-zero.
+template <int CC, int B>
+__device__ __forceinline__ void flush_batch(const CompositeParams &p, float *s_acc, const int *s_ids_b, int nb) {
+  constexpr int SHF = 3 * CC;
+  constexpr int ROWP = (SHF + 6 + 3) & ~3;
+  constexpr int NQ = ROWP / 4;
+  for (int e = threadIdx.x; e < nb * NQ; e += NTHREADS) {
+    const int j = e / NQ, q = e - NQ * j;
+    float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int w = 0; w < NWARPS; ++w) {
+      float4 *a4 = reinterpret_cast<float4 *>(s_acc + (w * B + j) * ROWP) + q;
+      float4 v = *a4;
+      s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+      *a4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    if (s.x == 0.f && s.y == 0.f && s.z == 0.f && s.w == 0.f) continue;
+    const size_t g = (size_t)s_ids_b[j];
+    const float sv4[4] = {s.x, s.y, s.z, s.w};
+    const int r0 = 4 * q;
+    if (CC % 4 == 0 && p.gsh_vec && r0 + 3 < SHF) {
+      const int c = r0 / CC, k = r0 - c * CC;
+      const size_t off = g * p.gsh_sg + c * p.gsh_sc + k;
+      if (p.g_sh_mc) {
+        multimem_red_add_v4(p.g_sh_mc + off, s);  // one instruction, the switch adds it on every GPU
+      } else if (p.n_peers > 0) {
+        for (int r = 0; r < p.n_peers; ++r) red_add_v4(p.g_sh_peer[r] + off, s);
+      } else {
+        red_add_v4(p.g_sh + off, s);
+      }
+    } else {
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int r = r0 + u;
+        const float val = sv4[u];
+        if (val == 0.f) continue;
+        if (r < SHF) {
+          const int c = r / CC, k = r - c * CC;
+          const size_t off = g * p.gsh_sg + c * p.gsh_sc + k;
+          if (p.n_peers > 0) {
+            for (int q2 = 0; q2 < p.n_peers; ++q2) atomicAdd(p.g_sh_peer[q2] + off, val);
+          } else {
+            atomicAdd(p.g_sh + off, val);
+          }
+        } else {
+          const int v = r - SHF;
+          if (v == 0) atomicAdd(p.g_mean + 2 * g, val);
+          else if (v == 1) atomicAdd(p.g_mean + 2 * g + 1, val);
+          else if (v == 2) atomicAdd(p.g_cov + 4 * g, val);
+          else if (v == 3) { atomicAdd(p.g_cov + 4 * g + 1, val); atomicAdd(p.g_cov + 4 * g + 2, val); }
+          else if (v == 4) atomicAdd(p.g_cov + 4 * g + 3, val);
+          else if (v == 5) atomicAdd(p.g_alpha + g, val);
+        }
+      }
+    }
+  }
+}
+
+// Same id-ring pipeline as the forward.  The warp-private accumulators are double-buffered: the
+// flush of batch b-1 (sum over warps + global reductions) is issued right after the barrier that
+// starts batch b, so one barrier per batch orders staging, accumulation and flush.
 template <int C, int B, bool EXACT>
 __global__ void __launch_bounds__(NTHREADS, (B <= 16 ? 3 : 2))
 composite_bwd_kernel(const CompositeParams p) {
@@ -363,14 +501,14 @@ composite_bwd_kernel(const CompositeParams p) {
   constexpr int SHF = 3 * CC;
   constexpr int ROW = SHF + 6;            // 3*CC SH sums, then gmx gmy g00 g01 g11 galpha
   constexpr int ROWP = (ROW + 3) & ~3;    // padded to float4
-  constexpr int NQ = ROWP / 4;
   constexpr int KL = CC < 16 ? CC : 16;   // lanes per half that own an SH column
+  constexpr int ACC = NWARPS * B * ROWP;  // floats per accumulator buffer
   extern __shared__ __align__(16) unsigned char smem_raw[];
   float4 *s_rec = reinterpret_cast<float4 *>(smem_raw);           // [2][B][3]
   float *s_sh = reinterpret_cast<float *>(s_rec + 2 * B * 3);     // [2][B][SHF]
-  float *s_w = s_sh + 2 * B * SHF;                                // [NWARPS][9][32]
-  float *s_acc = s_w + NWARPS * 9 * 32;                           // [NWARPS][B][ROWP]
-  int *s_ids = reinterpret_cast<int *>(s_acc + NWARPS * B * ROWP);  // [2][B]
+  float *s_w = s_sh + 2 * B * SHF;                                // [NWARPS][9][WROW]
+  float *s_acc = s_w + NWARPS * 9 * WROW;                         // [2][NWARPS][B][ROWP]
+  int *s_ids = reinterpret_cast<int *>(s_acc + 2 * ACC);          // [4][B] (ring; the flush reads slot cb-1)
 
   const int tile_id = blockIdx.x;
   const int tile_y = tile_id / p.ntw, tile_x = tile_id - tile_y * p.ntw;
@@ -386,67 +524,82 @@ composite_bwd_kernel(const CompositeParams p) {
   if (n_this <= 0) return;
 
   const float px = p.topleft[0] + gx * p.psx, py = p.topleft[1] + gy * p.psy;
-  float Y[CC];
-  pixel_basis<C>(p.c2w, px, py, Y);
-
-  // Yt[i] = Y_k(pixel 16*half + i) for this lane's (k = lane & 15, half = lane >> 4):
-  // transposed through the (not yet used) accumulator area.
+  Basis<CC> Y;
+  // Yt = Y_k(pixel 16*half + i), i = 0..15, for this lane's (k = lane & 15, half = lane >> 4):
+  // transposed through the (not yet used) accumulator area, kept as packed pairs.
   const int kcol = lane & 15, half = lane >> 4;
-  float Yt[16];
+  f32x2 Yt[8];
   {
+    float Yf[CC];
+    pixel_basis<C>(p.c2w, px, py, Yf);
+    Y.set(Yf);
     constexpr int TS = CC + 1;            // [32][CC+1] per warp; 32*(CC+1) <= B*ROWP for B >= 16
     float *tr = s_acc + warp * 32 * TS;
 #pragma unroll
-    for (int k = 0; k < CC; ++k) tr[lane * TS + k] = inside ? Y[k] : 0.0f;
+    for (int k = 0; k < CC; ++k) tr[lane * TS + k] = inside ? Yf[k] : 0.0f;
     __syncwarp();
 #pragma unroll
-    for (int i = 0; i < 16; ++i) Yt[i] = (kcol < CC) ? tr[(16 * half + i) * TS + kcol] : 0.0f;
+    for (int i = 0; i < 8; ++i) {
+      const float lo = (kcol < CC) ? tr[(16 * half + 2 * i) * TS + kcol] : 0.0f;
+      const float hi = (kcol < CC) ? tr[(16 * half + 2 * i + 1) * TS + kcol] : 0.0f;
+      Yt[i] = pack2(lo, hi);
+    }
   }
   __syncthreads();
-  for (int e = threadIdx.x; e < NWARPS * B * ROWP; e += NTHREADS) s_acc[e] = 0.0f;
+  for (int e = threadIdx.x; e < 2 * ACC; e += NTHREADS) s_acc[e] = 0.0f;
 
+  // f* = colour still to come after the current Gaussian (the reference's `final - prefix`,
+  // vol_render_sh.h:336-342), kept as a running remainder instead of final and prefix separately
   float g0 = 0.f, g1 = 0.f, g2 = 0.f, f0 = 0.f, f1 = 0.f, f2 = 0.f;
   if (inside) {
     g0 = p.grad_out[3 * pix + 0]; g1 = p.grad_out[3 * pix + 1]; g2 = p.grad_out[3 * pix + 2];
     f0 = p.out_saved[3 * pix + 0]; f1 = p.out_saved[3 * pix + 1]; f2 = p.out_saved[3 * pix + 2];
   }
-  float T = 1.0f, o0 = 0.0f, o1 = 0.0f, o2 = 0.0f;
+  float T = 1.0f;
   const float thresh = p.thresh;
   bool alive = inside && !(1.0f < thresh);
   const int32_t *ids = p.ids + first;
   const int n_batches = (n_this + B - 1) / B;
   constexpr float INV_K = 1.0f / (-0.5f * 1.4426950408889634f);  // undo the conic pre-scale
+  const bool id_lane = threadIdx.x < B;
 
   // per-lane shared addresses used by the warp reduction (computed once)
-  const uint32_t w_base = smem_u32(s_w + warp * 9 * 32);
+  const uint32_t w_base = smem_u32(s_w + warp * 9 * WROW);
   const uint32_t w_st = w_base + 4 * lane;                 // this lane's column in each of the 9 rows
   const uint32_t w_sh = w_base + 4 * (16 * half);          // SH GEMV: 16 pixels of this lane's half
   const int sv_row = lane >> 2, sv_q = lane & 3;           // scalar sums: row 3 + sv_row, quarter sv_q
-  const uint32_t w_sc = w_base + 4 * ((3 + (sv_row < 6 ? sv_row : 0)) * 32 + 8 * sv_q);
-  const uint32_t acc_base = smem_u32(s_acc + warp * B * ROWP);
+  const uint32_t w_sc = w_base + 4 * ((3 + (sv_row < 6 ? sv_row : 0)) * WROW + 8 * sv_q);
+  const uint32_t acc_warp = 4 * (warp * B * ROWP);
 
-  int my_id = (threadIdx.x < B && threadIdx.x < n_this) ? ids[threadIdx.x] : 0;
-  for (int b = 0; b <= n_batches; ++b) {
-    if (b < n_batches) {
-      const int buf = b & 1;
-      const int nb = min(B, n_this - b * B);
-      if (threadIdx.x < B) s_ids[buf * B + threadIdx.x] = my_id;
-      __syncthreads();  // ids visible; previous flush (acc zeroing) complete
-      int nxt = (b + 1) * B + threadIdx.x;
-      my_id = (threadIdx.x < B && nxt < n_this) ? ids[nxt] : 0;
-      stage_batch<CC, B>(p, s_ids + buf * B, nb, s_rec + buf * B * 3, s_sh + buf * B * SHF);
-    }
-    cp_async_commit();
-    if (b == 0) continue;
-    cp_async_wait<1>();
-    __syncthreads();
-    const int cb = b - 1;
+  // prologue: ids of batch 0 -> ring slot 0, batch 0 in flight, ids of batch 1 -> ring slot 1
+  if (id_lane) s_ids[threadIdx.x] = threadIdx.x < n_this ? ids[threadIdx.x] : 0;
+  int my_id = (id_lane && B + threadIdx.x < n_this) ? ids[B + threadIdx.x] : 0;
+  __syncthreads();  // ids visible, accumulators zeroed
+  stage_batch<CC, B>(p, s_ids, min(B, n_this), s_rec, s_sh);
+  cp_async_commit();
+  if (id_lane) s_ids[B + threadIdx.x] = my_id;
+  my_id = (id_lane && 2 * B + threadIdx.x < n_this) ? ids[2 * B + threadIdx.x] : 0;
+
+  for (int cb = 0;; ++cb) {
+    cp_async_wait<0>();
+    // one barrier per batch: batch cb has landed, every warp is done with batch cb-1, ring slot
+    // published; the vote ends the tile when every pixel is saturated
+    const bool stop = __syncthreads_and(!alive) || cb == n_batches;
     const int buf = cb & 1;
+    if (!stop && cb + 1 < n_batches) {
+      const int nbuf = buf ^ 1;
+      stage_batch<CC, B>(p, s_ids + ((cb + 1) & 3) * B, min(B, n_this - (cb + 1) * B), s_rec + nbuf * B * 3,
+                         s_sh + nbuf * B * SHF);
+      cp_async_commit();
+    }
+    // flush of the previous batch (complete: every warp passed the barrier above after it)
+    if (cb > 0) flush_batch<CC, B>(p, s_acc + (buf ^ 1) * ACC, s_ids + ((cb - 1) & 3) * B, B);
+    if (stop) break;
     const int nb = min(B, n_this - cb * B);
     {
       uint32_t rec_a = smem_u32(s_rec + buf * B * 3);
       uint32_t sh_a = smem_u32(s_sh + buf * B * SHF);
-      uint32_t row_a = acc_base;
+      uint32_t row_a = smem_u32(s_acc + buf * ACC) + acc_warp;
       for (int j = 0; j < nb; ++j, rec_a += 48, sh_a += 4 * SHF, row_a += 4 * ROWP) {
         if ((j & 7) == 0 && !__any_sync(0xffffffffu, alive)) break;
         float w0 = 0.f, w1 = 0.f, w2 = 0.f, gmx = 0.f, gmy = 0.f, g00 = 0.f, g01 = 0.f, g11 = 0.f,
@@ -462,20 +615,20 @@ composite_bwd_kernel(const CompositeParams p) {
             float coeff = (a * T) * G;
             if (isnan(coeff)) coeff = 0.0f;
             float y[3];
-            sh_colour<CC>(sh_a, Y, coeff, y);
-            o0 = fmaf(coeff, y[0], o0);
-            o1 = fmaf(coeff, y[1], o1);
-            o2 = fmaf(coeff, y[2], o2);
+            sh_colour<CC>(sh_a, Y, y);
+            f0 = fmaf(-coeff, y[0], f0);
+            f1 = fmaf(-coeff, y[1], f1);
+            f2 = fmaf(-coeff, y[2], f2);
             // vol_render_sh.h:328-333
             w0 = coeff * (y[0] * (1.0f - y[0])) * g0;
             w1 = coeff * (y[1] * (1.0f - y[1])) * g1;
             w2 = coeff * (y[2] * (1.0f - y[2])) * g2;
             // vol_render_sh.h:336-342
             const float one_m = 1.0f - aG;
-            const float inv1m = rcp_approx(one_m);
-            float P = g0 * fmaf(y[0], T, -(f0 - o0) * inv1m);
-            P = fmaf(g1, fmaf(y[1], T, -(f1 - o1) * inv1m), P);
-            P = fmaf(g2, fmaf(y[2], T, -(f2 - o2) * inv1m), P);
+            const float inv1m = -rcp_approx(one_m);
+            float P = g0 * fmaf(y[0], T, f0 * inv1m);
+            P = fmaf(g1, fmaf(y[1], T, f1 * inv1m), P);
+            P = fmaf(g2, fmaf(y[2], T, f2 * inv1m), P);
             // kernels.h:394-418 with the inverse covariance recovered from the conic
             const float dx = px - r0.x, dy = py - r0.y;
             const float i00 = r1.x * INV_K, i11 = r1.z * INV_K, i01 = (-0.5f * INV_K) * r1.y;
@@ -494,29 +647,31 @@ composite_bwd_kernel(const CompositeParams p) {
         }
         if (!__any_sync(0xffffffffu, contrib)) continue;
         // ---- warp reduction over the 32 pixels through shared memory
-        sts32(w_st + 4 * 0 * 32, w0);
-        sts32(w_st + 4 * 1 * 32, w1);
-        sts32(w_st + 4 * 2 * 32, w2);
-        sts32(w_st + 4 * 3 * 32, gmx);
-        sts32(w_st + 4 * 4 * 32, gmy);
-        sts32(w_st + 4 * 5 * 32, g00);
-        sts32(w_st + 4 * 6 * 32, g01);
-        sts32(w_st + 4 * 7 * 32, g11);
-        sts32(w_st + 4 * 8 * 32, ga);
+        sts32(w_st + 4 * 0 * WROW, w0);
+        sts32(w_st + 4 * 1 * WROW, w1);
+        sts32(w_st + 4 * 2 * WROW, w2);
+        sts32(w_st + 4 * 3 * WROW, gmx);
+        sts32(w_st + 4 * 4 * WROW, gmy);
+        sts32(w_st + 4 * 5 * WROW, g00);
+        sts32(w_st + 4 * 6 * WROW, g01);
+        sts32(w_st + 4 * 7 * WROW, g11);
+        sts32(w_st + 4 * 8 * WROW, ga);
         __syncwarp();
-        float a0 = 0.f, a1 = 0.f, a2 = 0.f;
+        f32x2 A0 = 0ull, A1 = 0ull, A2 = 0ull;
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
-          const float4 va = lds128(w_sh + 16 * q);
-          const float4 vb = lds128(w_sh + 4 * 32 + 16 * q);
-          const float4 vc = lds128(w_sh + 8 * 32 + 16 * q);
-          a0 = fmaf(va.x, Yt[4 * q], a0); a0 = fmaf(va.y, Yt[4 * q + 1], a0);
-          a0 = fmaf(va.z, Yt[4 * q + 2], a0); a0 = fmaf(va.w, Yt[4 * q + 3], a0);
-          a1 = fmaf(vb.x, Yt[4 * q], a1); a1 = fmaf(vb.y, Yt[4 * q + 1], a1);
-          a1 = fmaf(vb.z, Yt[4 * q + 2], a1); a1 = fmaf(vb.w, Yt[4 * q + 3], a1);
-          a2 = fmaf(vc.x, Yt[4 * q], a2); a2 = fmaf(vc.y, Yt[4 * q + 1], a2);
-          a2 = fmaf(vc.z, Yt[4 * q + 2], a2); a2 = fmaf(vc.w, Yt[4 * q + 3], a2);
+          f32x2 lo, hi;
+          lds128_2(w_sh + 16 * q, lo, hi);
+          A0 = fma2(lo, Yt[2 * q], A0);
+          A0 = fma2(hi, Yt[2 * q + 1], A0);
+          lds128_2(w_sh + 4 * WROW + 16 * q, lo, hi);
+          A1 = fma2(lo, Yt[2 * q], A1);
+          A1 = fma2(hi, Yt[2 * q + 1], A1);
+          lds128_2(w_sh + 8 * WROW + 16 * q, lo, hi);
+          A2 = fma2(lo, Yt[2 * q], A2);
+          A2 = fma2(hi, Yt[2 * q + 1], A2);
         }
+        float a0 = sum2(A0), a1 = sum2(A1), a2 = sum2(A2);
         // six scalar sums: lane = 4*v + qd sums pixels 8*qd .. 8*qd+7 of row 3+v
         float sv;
         {
@@ -541,76 +696,29 @@ composite_bwd_kernel(const CompositeParams p) {
         }
       }
     }
-    __syncthreads();
-    // ---- flush: sum the 8 warp-private rows, reduce into global memory, re-zero
-    for (int e = threadIdx.x; e < nb * NQ; e += NTHREADS) {
-      const int j = e / NQ, q = e - NQ * j;
-      float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-      for (int w = 0; w < NWARPS; ++w) {
-        float4 *a4 = reinterpret_cast<float4 *>(s_acc + (w * B + j) * ROWP) + q;
-        float4 v = *a4;
-        s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
-        *a4 = make_float4(0.f, 0.f, 0.f, 0.f);
-      }
-      if (s.x == 0.f && s.y == 0.f && s.z == 0.f && s.w == 0.f) continue;
-      const size_t g = (size_t)s_ids[buf * B + j];
-      const float sv4[4] = {s.x, s.y, s.z, s.w};
-      const int r0 = 4 * q;
-      if (CC % 4 == 0 && p.gsh_vec && r0 + 3 < SHF) {
-        const int c = r0 / CC, k = r0 - c * CC;
-        const size_t off = g * p.gsh_sg + c * p.gsh_sc + k;
-        if (p.g_sh_mc) {
-          multimem_red_add_v4(p.g_sh_mc + off, s);  // one instruction, the switch adds it on every GPU
-        } else if (p.n_peers > 0) {
-          for (int r = 0; r < p.n_peers; ++r) red_add_v4(p.g_sh_peer[r] + off, s);
-        } else {
-          red_add_v4(p.g_sh + off, s);
-        }
-      } else {
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          const int r = r0 + u;
-          const float val = sv4[u];
-          if (val == 0.f) continue;
-          if (r < SHF) {
-            const int c = r / CC, k = r - c * CC;
-            const size_t off = g * p.gsh_sg + c * p.gsh_sc + k;
-            if (p.n_peers > 0) {
-              for (int q2 = 0; q2 < p.n_peers; ++q2) atomicAdd(p.g_sh_peer[q2] + off, val);
-            } else {
-              atomicAdd(p.g_sh + off, val);
-            }
-          } else {
-            const int v = r - SHF;
-            if (v == 0) atomicAdd(p.g_mean + 2 * g, val);
-            else if (v == 1) atomicAdd(p.g_mean + 2 * g + 1, val);
-            else if (v == 2) atomicAdd(p.g_cov + 4 * g, val);
-            else if (v == 3) { atomicAdd(p.g_cov + 4 * g + 1, val); atomicAdd(p.g_cov + 4 * g + 2, val); }
-            else if (v == 4) atomicAdd(p.g_cov + 4 * g + 3, val);
-            else if (v == 5) atomicAdd(p.g_alpha + g, val);
-          }
-        }
-      }
+    if (cb + 1 < n_batches) {
+      if (id_lane) s_ids[((cb + 2) & 3) * B + threadIdx.x] = my_id;
+      const int nxt = (cb + 3) * B + threadIdx.x;
+      my_id = (id_lane && nxt < n_this) ? ids[nxt] : 0;
     }
-    if (__syncthreads_and(!alive)) break;
   }
   cp_async_wait<0>();
 }
+
 
 // ---------------------------------------------------------------- host side
 
 template <int C, int B>
 static size_t fwd_smem() {
   return (size_t)2 * B * 3 * sizeof(float4) + (size_t)2 * B * 3 * C * C * sizeof(float) +
-         (size_t)2 * B * sizeof(int);
+         (size_t)3 * B * sizeof(int);
 }
 template <int C, int B>
 static size_t bwd_smem() {
   constexpr int ROWP = (3 * C * C + 6 + 3) & ~3;
   return (size_t)2 * B * 3 * sizeof(float4) + (size_t)2 * B * 3 * C * C * sizeof(float) +
-         (size_t)NWARPS * 9 * 32 * sizeof(float) + (size_t)NWARPS * B * ROWP * sizeof(float) +
-         (size_t)2 * B * sizeof(int);
+         (size_t)NWARPS * 9 * WROW * sizeof(float) + (size_t)2 * NWARPS * B * ROWP * sizeof(float) +
+         (size_t)4 * B * sizeof(int);
 }
 
 constexpr int FWD_B = 64;
@@ -689,9 +797,11 @@ int gs3d_composite_sh_forward(uint32_t M, const float *records, const float *sh_
   p.sh_vec = (CC % 4 == 0) && (sh_stride_g % 4 == 0) && (sh_stride_c % 4 == 0) && aligned16(sh_coeffs);
   cudaStream_t st = as_stream(stream);
   switch (C) {
+#ifndef GS3D_ONLY_C4  // (experimental builds compile the C = 4 kernels only)
     case 1: return launch_fwd<1>(p, n_tiles, st);
     case 2: return launch_fwd<2>(p, n_tiles, st);
     case 3: return launch_fwd<3>(p, n_tiles, st);
+#endif
     default: return launch_fwd<4>(p, n_tiles, st);
   }
 }
@@ -741,9 +851,11 @@ int gs3d_composite_sh_backward_peers(uint32_t M, const float *records, const flo
   p.g_sh_mc = (multicast_grad_sh && p.gsh_vec && n_peers > 0) ? static_cast<float *>(multicast_grad_sh) : nullptr;
   cudaStream_t st = as_stream(stream);
   switch (C) {
+#ifndef GS3D_ONLY_C4
     case 1: return launch_bwd<1>(p, n_tiles, st);
     case 2: return launch_bwd<2>(p, n_tiles, st);
     case 3: return launch_bwd<3>(p, n_tiles, st);
+#endif
     default: return launch_bwd<4>(p, n_tiles, st);
   }
 }
