@@ -31,6 +31,14 @@ constexpr int NTHREADS = 256;
 constexpr int NWARPS = 8;
 constexpr float MIN_RENDER_ALPHA = 1 / 255.0f;  // common.h:90
 constexpr float DECISION_MARGIN = 0.004f;       // log2 units around the skip threshold
+constexpr float DEAD = 1e30f;                   // bias that makes a finished pixel fail the skip test
+#ifndef GS3D_UNROLL_F
+#define GS3D_UNROLL_F 4
+#endif
+#ifndef GS3D_UNROLL_B
+#define GS3D_UNROLL_B 2
+#endif
+constexpr int UF = GS3D_UNROLL_F, UB = GS3D_UNROLL_B;  // inner-loop unroll (forward, backward); divide 4
 
 struct CompositeParams {
   const float4 *records;
@@ -194,25 +202,31 @@ __device__ __forceinline__ float gaussian_exact(float x, float y, float4 cv) {
   return expf(arg);
 }
 
-// Skip decision for one (pixel, Gaussian) pair.  r0 = {m.x, m.y, alpha_, log2 threshold},
+// Skip decision for one (pixel, Gaussian) pair (pair_test + pair_decide).  r0 = {m.x, m.y, alpha_, log2 threshold},
 // r1 = {qa, qb, qc, depth}.  Returns true when the pair contributes (alpha_*G >= 1/255) and then
 // G is valid.  Far from the threshold the pre-scaled conic decides alone (no exponential for
 // skipped pairs); within DECISION_MARGIN (or for a non-negative exponent, where the reference's
 // `radial < 0 -> 1000` rule matters) the reference's exact arithmetic decides.
-template <bool EXACT>
-__device__ __forceinline__ bool eval_pair(float px, float py, const float4 r0, const float4 r1,
-                                          uint32_t cov_addr, float &G) {
+// Part 1: log2 G and its distance to the per-Gaussian threshold.
+__device__ __forceinline__ float4 pair_test(float px, float py, uint32_t rec_addr, float &pw, float &diff) {
+  const float4 r0 = lds128(rec_addr), r1 = lds128(rec_addr + 16);
   const float dx = px - r0.x, dy = py - r0.y;
   const float u = fmaf(r1.y, dy, r1.x * dx);
-  const float pw = fmaf(r1.z * dy, dy, dx * u);  // log2 G
-  const float diff = pw - r0.w;
-  if (diff < -DECISION_MARGIN) return false;     // the common case: clearly below 1/255
+  pw = fmaf(r1.z * dy, dy, dx * u);  // log2 G
+  diff = pw - r0.w;
+  return r0;
+}
+// Part 2, only reached when part 1 did not clearly reject: decide, and produce G.
+template <bool EXACT>
+__device__ __forceinline__ bool pair_decide(float px, float py, float dead, float pw, float diff,
+                                            const float4 r0, uint32_t cov_addr, float &G) {
+  if (dead != 0.0f) return false;                // finished pixel that slipped through (non-finite record)
   if (diff >= DECISION_MARGIN && pw <= -1e-5f) {
     G = ex2_approx(pw);
     return true;
   }
   if (EXACT) {
-    const float val = gaussian_exact(dx, dy, lds128(cov_addr));
+    const float val = gaussian_exact(px - r0.x, py - r0.y, lds128(cov_addr));
     G = val;
     return !(r0.z * val < MIN_RENDER_ALPHA);
   }
@@ -229,6 +243,13 @@ __device__ __forceinline__ void stage_batch(const CompositeParams &p, const int 
   for (int e = threadIdx.x; e < nb * 3; e += NTHREADS) {
     int j = e / 3, r = e - 3 * j;
     cp_async_16(s_rec + e, p.records + 3 * (size_t)s_ids[j] + r);
+  }
+  // the compositing loops are unrolled by up to 4: pad with null records (threshold +inf: never
+  // contributes) so they need no remainder handling
+  if (threadIdx.x >= NTHREADS - 9) {
+    const int e = nb * 3 + (NTHREADS - 1 - threadIdx.x);
+    if (e < ((nb + 3) & ~3) * 3)
+      s_rec[e] = (e % 3 == 0) ? make_float4(0.f, 0.f, 0.f, __int_as_float(0x7f800000)) : make_float4(0.f, 0.f, 0.f, 0.f);
   }
   if (p.sh_vec) {
     constexpr int V = SHF / 4 > 0 ? SHF / 4 : 1;
@@ -318,8 +339,11 @@ __device__ __forceinline__ void sh_colour(uint32_t h_addr, const Basis<CC> &Y, f
 // buffer batch b-1 used, (iii) publishes the id ring slot and (iv) carries the "every pixel of the
 // tile is saturated" vote that ends the tile early.
 
+#ifndef GS3D_FWD_MINB
+#define GS3D_FWD_MINB 4  // CTAs per SM the forward is compiled for (64 registers)
+#endif
 template <int C, int B, bool EXACT>
-__global__ void __launch_bounds__(NTHREADS)
+__global__ void __launch_bounds__(NTHREADS, GS3D_FWD_MINB)
 composite_fwd_kernel(const CompositeParams p) {
   constexpr int CC = C * C;
   constexpr int SHF = 3 * CC;
@@ -364,7 +388,8 @@ composite_fwd_kernel(const CompositeParams p) {
   float T = 1.0f, o0 = 0.0f, o1 = 0.0f, o2 = 0.0f;
   int last = 0;
   const float thresh = p.thresh;
-  bool alive = inside && !(1.0f < thresh);  // the reference tests T (initially 1) before each Gaussian
+  // the reference tests T (initially 1) before each Gaussian
+  float dead = (inside && !(1.0f < thresh)) ? 0.0f : DEAD;
   const int32_t *ids = p.ids + first;
   const int n_batches = (n_this + B - 1) / B;
   const bool id_lane = threadIdx.x < B;
@@ -380,7 +405,7 @@ composite_fwd_kernel(const CompositeParams p) {
 
   for (int cb = 0; cb < n_batches; ++cb) {
     cp_async_wait<0>();
-    if (__syncthreads_and(!alive)) break;  // all pixels of the tile finished -> stop staging
+    if (__syncthreads_and(dead != 0.0f)) break;  // all pixels of the tile finished -> stop staging
     const int buf = cb & 1;
     if (cb + 1 < n_batches) {
       const int nbuf = buf ^ 1;
@@ -394,24 +419,32 @@ composite_fwd_kernel(const CompositeParams p) {
     const int nb = min(B, n_this - cb * B);
     uint32_t rec_a = smem_u32(s_rec + buf * B * 3);
     uint32_t sh_a = smem_u32(s_sh + buf * B * SHF);
-    for (int j = 0; j < nb; ++j, rec_a += 48, sh_a += 4 * SHF) {
-      if ((j & 7) == 0 && !__any_sync(0xffffffffu, alive)) break;
-      if (!alive) continue;
-      const float4 r0 = lds128(rec_a), r1 = lds128(rec_a + 16);
-      float G;
-      if (!eval_pair<EXACT>(px, py, r0, r1, rec_a + 32, G)) continue;
-      const float a = r0.z;
-      float coeff = (a * T) * G;
-      if (isnan(coeff)) coeff = 0.0f;
-      float y[3];
-      sh_colour<CC>(sh_a, Y, y);
-      o0 = fmaf(coeff, y[0], o0);
-      o1 = fmaf(coeff, y[1], o1);
-      o2 = fmaf(coeff, y[2], o2);
-      T *= (1 - a * G);
-      last = cb * B + j + 1;
-      // vol_render_sh.h:121-123 tests T before each Gaussian; T only changes here
-      if (T < thresh) alive = false;
+    for (int j = 0; j < nb; j += UF, rec_a += 48 * UF, sh_a += 4 * SHF * UF) {
+      if (!__any_sync(0xffffffffu, dead == 0.0f)) break;
+#pragma unroll
+      for (int u = 0; u < UF; ++u) {
+        // (testing the whole unroll group up front for ILP measured slower: 0.502 vs 0.492 ms)
+        float pw, df;
+        const float4 r0 = pair_test(px, py, rec_a + 48 * u, pw, df);
+        // `dead` is 0 for a live pixel and 1e30 for a finished one (T < thresh, or outside the
+        // image): finished pixels fail the common-case test without a branch of their own
+        if (df - dead < -DECISION_MARGIN) continue;  // the common case: clearly below 1/255
+        float G;
+        if (pair_decide<EXACT>(px, py, dead, pw, df, r0, rec_a + 48 * u + 32, G)) {
+          const float a = r0.z;
+          float coeff = (a * T) * G;
+          if (isnan(coeff)) coeff = 0.0f;
+          float y[3];
+          sh_colour<CC>(sh_a + 4 * SHF * u, Y, y);
+          o0 = fmaf(coeff, y[0], o0);
+          o1 = fmaf(coeff, y[1], o1);
+          o2 = fmaf(coeff, y[2], o2);
+          T *= (1 - a * G);
+          last = cb * B + j + u + 1;
+          // vol_render_sh.h:121-123 tests T before each Gaussian; T only changes here
+          if (T < thresh) dead = DEAD;
+        }
+      }
     }
   }
   cp_async_wait<0>();
@@ -557,7 +590,7 @@ composite_bwd_kernel(const CompositeParams p) {
   }
   float T = 1.0f;
   const float thresh = p.thresh;
-  bool alive = inside && !(1.0f < thresh);
+  float dead = (inside && !(1.0f < thresh)) ? 0.0f : DEAD;
   const int32_t *ids = p.ids + first;
   const int n_batches = (n_this + B - 1) / B;
   constexpr float INV_K = 1.0f / (-0.5f * 1.4426950408889634f);  // undo the conic pre-scale
@@ -584,7 +617,7 @@ composite_bwd_kernel(const CompositeParams p) {
     cp_async_wait<0>();
     // one barrier per batch: batch cb has landed, every warp is done with batch cb-1, ring slot
     // published; the vote ends the tile when every pixel is saturated
-    const bool stop = __syncthreads_and(!alive) || cb == n_batches;
+    const bool stop = __syncthreads_and(dead != 0.0f) || cb == n_batches;
     const int buf = cb & 1;
     if (!stop && cb + 1 < n_batches) {
       const int nbuf = buf ^ 1;
@@ -600,22 +633,26 @@ composite_bwd_kernel(const CompositeParams p) {
       uint32_t rec_a = smem_u32(s_rec + buf * B * 3);
       uint32_t sh_a = smem_u32(s_sh + buf * B * SHF);
       uint32_t row_a = smem_u32(s_acc + buf * ACC) + acc_warp;
-      for (int j = 0; j < nb; ++j, rec_a += 48, sh_a += 4 * SHF, row_a += 4 * ROWP) {
-        if ((j & 7) == 0 && !__any_sync(0xffffffffu, alive)) break;
+      for (int j = 0; j < nb; j += UB, rec_a += 48 * UB, sh_a += 4 * SHF * UB, row_a += 4 * ROWP * UB) {
+       if (!__any_sync(0xffffffffu, dead == 0.0f)) break;
+#pragma unroll
+       for (int uu = 0; uu < UB; ++uu) {
         float w0 = 0.f, w1 = 0.f, w2 = 0.f, gmx = 0.f, gmy = 0.f, g00 = 0.f, g01 = 0.f, g11 = 0.f,
               ga = 0.f;
         bool contrib = false;
-        if (alive) {
-          const float4 r0 = lds128(rec_a), r1 = lds128(rec_a + 16);
+        float pw, df;
+        const float4 r1 = lds128(rec_a + 48 * uu + 16);
+        const float4 r0 = pair_test(px, py, rec_a + 48 * uu, pw, df);
+        if (!(df - dead < -DECISION_MARGIN)) {
           float G;
-          if (eval_pair<EXACT>(px, py, r0, r1, rec_a + 32, G)) {
+          if (pair_decide<EXACT>(px, py, dead, pw, df, r0, rec_a + 48 * uu + 32, G)) {
             contrib = true;
             const float a = r0.z;
             const float aG = a * G;
             float coeff = (a * T) * G;
             if (isnan(coeff)) coeff = 0.0f;
             float y[3];
-            sh_colour<CC>(sh_a, Y, y);
+            sh_colour<CC>(sh_a + 4 * SHF * uu, Y, y);
             f0 = fmaf(-coeff, y[0], f0);
             f1 = fmaf(-coeff, y[1], f1);
             f2 = fmaf(-coeff, y[2], f2);
@@ -642,10 +679,10 @@ composite_bwd_kernel(const CompositeParams p) {
             g11 = hg * vy * vy;
             ga = P * G;
             T *= one_m;
-            if (T < thresh) alive = false;  // vol_render_sh.h:296-298 (T only changes here)
+            if (T < thresh) dead = DEAD;  // vol_render_sh.h:296-298 (T only changes here)
           }
         }
-        if (!__any_sync(0xffffffffu, contrib)) continue;
+        if (__any_sync(0xffffffffu, contrib)) {
         // ---- warp reduction over the 32 pixels through shared memory
         sts32(w_st + 4 * 0 * WROW, w0);
         sts32(w_st + 4 * 1 * WROW, w1);
@@ -685,15 +722,17 @@ composite_bwd_kernel(const CompositeParams p) {
         sv += __shfl_xor_sync(0xffffffffu, sv, 1);
         sv += __shfl_xor_sync(0xffffffffu, sv, 2);
         if (lane < KL) {
-          const uint32_t ra = row_a + 4 * lane;
+          const uint32_t ra = row_a + 4 * ROWP * uu + 4 * lane;
           sts32(ra, lds32(ra) + a0);
           sts32(ra + 4 * CC, lds32(ra + 4 * CC) + a1);
           sts32(ra + 8 * CC, lds32(ra + 8 * CC) + a2);
         }
         if (sv_q == 0 && sv_row < 6) {
-          const uint32_t ra = row_a + 4 * (SHF + sv_row);
+          const uint32_t ra = row_a + 4 * ROWP * uu + 4 * (SHF + sv_row);
           sts32(ra, lds32(ra) + sv);
         }
+        }
+       }
       }
     }
     if (cb + 1 < n_batches) {
