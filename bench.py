@@ -37,9 +37,11 @@ def parse():
     ap.add_argument("--n-gaussians", type=int, default=None, help="override N (debugging)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-exact", action="store_true", help="disable exact skip decisions")
-    ap.add_argument("--dp-mode", default="fused", choices=["fused", "allreduce"],
+    ap.add_argument("--dp-mode", default="auto", choices=["auto", "pull", "push", "fused", "sparse", "allreduce"],
                     help="N>1: 'fused' = SH gradients reduced into all ranks by the backward kernel over "
-                         "NVLink/NVSwitch + small all-reduce; 'allreduce' = one dense NCCL all-reduce")
+                         "NVLink/NVSwitch + small all-reduce; 'sparse' = all-reduce of the union of touched "
+                         "rows only; 'allreduce' = one dense NCCL all-reduce; 'push' (= 'auto') = each rank "
+                         "adds the rows it touched into every rank's result buffer over NVSwitch multicast")
     return ap.parse_args()
 
 
@@ -112,6 +114,25 @@ def views_for(world, torch):
                             [-math.sin(a), 0.0, math.cos(a), 0.0]], dtype=torch.float32)
         out.append(c2w)
     return out
+
+
+def dp_exchange_desc(flat, world, N):
+    if world == 1 or flat is None:
+        return None
+    if flat.pull:
+        how = ("multimem.ld_reduce (summed in the NVSwitch) + multimem.st" if flat.multicast_ptr
+               else "peer loads + peer stores over NVLink")
+        return f"sparse all-reduce of the union of touched rows (240 B each) over symmetric memory: {how}"
+    if flat.push:
+        how = ("multimem.red on the NVSwitch multicast address" if flat.multicast_ptr
+               else "red.global.add per peer over NVLink")
+        return f"each rank pushes the rows it touched (240 B each) into every rank's result buffer: {how}"
+    if flat.fused:
+        return "in-kernel multimem/peer reduction of SH grads + 132 MB all-reduce"
+    if flat.sparse:
+        return (f"NCCL all-reduce of the union of touched rows ({flat.last_union_rows} of {N} rows x 240 B) "
+                "+ 3 MB mark all-reduce")
+    return "dense 708 MB NCCL all-reduce"
 
 
 def peaks():
@@ -187,7 +208,9 @@ def run_ours(args, rank, local_rank, world):
         # summed over the ranks with a single NCCL all-reduce per step
         from gaussian_splatting_3d_b200 import parallel as P
 
-        flat = P.FlatGradients(r, fused=(args.dp_mode == "fused")).attach(r)
+        mode = args.dp_mode if args.dp_mode != "auto" else "pull"
+        flat = P.FlatGradients(r, fused=(mode == "fused"), sparse=(mode == "sparse"), push=(mode == "push"),
+                               pull=(mode == "pull")).attach(r)
 
     def step(e2e):
         if e2e:
@@ -266,16 +289,36 @@ def run_ours(args, rank, local_rank, world):
 
     for fname, label in (("project_cull_fused", "K1_project_cull"), ("tile_culling_aabb_start_end", "K2_binning"),
                          ("composite_sh_forward", "K3_composite_fwd"), ("composite_sh_backward", "K4a_composite_bwd"),
-                         ("project_backward_fused", "K4b_project_bwd")):
+                         ("project_backward_fused", "K4b_project_bwd"), ("rows_push_marked", "X_rows_push"),
+                         ("rows_pull_marked", "X_rows_pull"), ("marks_broadcast", "X_marks_broadcast"),
+                         ("rows_zero_marked", "X_rows_zero")):
         wrap(fname, label)
+    if flat is not None:  # the data-parallel exchange: per-step reset (+ barrier) and exchange (+ barrier)
+        for meth, label in (("zero", "DP_reset"), ("exchange", "DP_exchange")):
+            def timed_method(f=getattr(flat, meth), label=label):
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                out = f()
+                e1.record()
+                stage_ms.setdefault(label, []).append((e0, e1))
+                return out
+            setattr(flat, meth, timed_method)
     n_prof = min(args.steps, 10)
     for _ in range(n_prof):
         step(False)
     torch.cuda.synchronize()
     for fname, f in orig.items():
         setattr(ops, fname, f)
-    kernels_ms = {k: sum(a.elapsed_time(b) for a, b in v) / len(v) for k, v in stage_ms.items()}
+    if flat is not None:
+        del flat.zero, flat.exchange  # drop the instance-level wrappers
+    kernels_ms = {k: sum(a.elapsed_time(b) for a, b in v) / n_prof for k, v in stage_ms.items()}  # per step
 
+    rank_kernel_ms = None
+    if world > 1:  # per-rank sum of the hot-path kernels: shows how uneven the views' work is
+        mine = torch.tensor([sum(v for k, v in kernels_ms.items() if k.startswith("K"))], device=dev)
+        allr = [torch.zeros_like(mine) for _ in range(world)]
+        dist.all_gather(allr, mine)
+        rank_kernel_ms = [round(float(t.item()), 4) for t in allr]
     n_dub = r.total_dub_gaussians
     ms_step = ms_total / args.steps
     value = world * 1000.0 / ms_step
@@ -287,7 +330,8 @@ def run_ours(args, rank, local_rank, world):
     px = cam.w * cam.h
     bytes_fwd = n_dub * (4 + 48 + 12 * CC) + px * 12
     bytes_bwd = n_dub * (4 + 48 + 12 * CC) + px * 36 + N * 4 * (7 + 3 * CC)
-    dom = max(kernels_ms, key=kernels_ms.get) if kernels_ms else None
+    kk = {k: v for k, v in kernels_ms.items() if k.startswith("K")}
+    dom = max(kk, key=kk.get) if kk else None
     algo = {"K3_composite_fwd": bytes_fwd, "K4a_composite_bwd": bytes_bwd, "K1_project_cull": N * (48 + 101),
             "K2_binning": N * (4 + 4 * 24 + 8) + n_dub * (8 + 2 * 24 + 4), "K4b_project_bwd": N * (48 + 28 + 44 + 1)}
     roofline = None
@@ -305,13 +349,12 @@ def run_ours(args, rank, local_rank, world):
         "config": {"workload": f"{name}: {N} Gaussians, SH degree {C - 1} (C={C}), {cam.w}x{cam.h}, "
                                f"1 view/step/GPU, fwd + L2 loss + bwd", "n_dub": n_dub,
                    "views_per_step": world, "parallelism": f"dp{world}" if world > 1 else "single",
-                   "dp_exchange": (None if world == 1 else
-                                   ("in-kernel multimem/peer reduction of SH grads + 132 MB all-reduce"
-                                    if flat.fused else "dense 708 MB NCCL all-reduce")),
+                   "dp_exchange": dp_exchange_desc(flat, world, N),
                    "l2_policy": "inputs larger than L2 (parameters 708 MB, duplicates 132 MB vs 126 MB L2)",
                    "exact_decisions": not args.no_exact},
         "fwd_fps": world * 1000.0 * args.steps / ms_fwd,
         "kernels_ms": kernels_ms,
+        "rank_kernel_ms": rank_kernel_ms,
         "roofline": roofline,
         "e2e": {"value": world * 1000.0 * args.steps / ms_e2e, "unit": "iters/s",
                 "h2d_bytes_per_step": int(c2w_host.numel() * 4 + tgt_host.numel() * 4), "d2h_bytes_per_step": 4},

@@ -56,7 +56,16 @@ SIGNATURES = {
                                         _u32, _f, _i, _P]),
     "gs3d_composite_sh_backward_peers": (_i, [_u32, _P, _P, _u32, _u32, _P, _P, _P, _P, _P, _P, _P, _P,
                                               _u32, _u32, _P, _P, _P, _u32, _u32, _u32, _f, _f, _u32, _u32,
-                                              _u32, _f, _i, _P, _i, _P, _P]),
+                                              _u32, _f, _i, _P, _i, _P, _P, _P]),
+    "gs3d_rows_gather": (_i, [_i, _P, _P, _P, _u32, _P, _u32, _P]),
+    "gs3d_rows_scatter": (_i, [_i, _P, _P, _P, _u32, _P, _u32, _P]),
+    "gs3d_rows_push_marked": (_i, [_P, _u32, _i, _P, _P, _P, _P, _P, _i, _P, _P]),
+    "gs3d_rows_zero_marked": (_i, [_P, _u32, _i, _P, _P, _i, _P]),
+    "gs3d_marks_broadcast": (_i, [_P, _u32, _P, _i, _P]),
+    "gs3d_row_duplicate_counts": (_i, [_u32, _P, _P, _u32, _P, _P, _sz, _P]),
+    "gs3d_clip_scratch_bytes": (_sz, [_u32]),
+    "gs3d_clip_rects_to_rows": (_i, [_u32, _P, _P, _P, _i, _i, _P, _P, _P, _P, _I64P, _P, _sz, _P]),
+    "gs3d_rows_pull_marked": (_i, [_P, _u32, _i, _P, _P, _P, _P, _i, _i, _P, _P, _P]),
     "gs3d_project_backward_fused": (_i, [_u32, _P, _P, _P, _P, _P, _i, _i, _P, _i, _P, _P, _P, _P, _P,
                                          _P, _P, _P, _i, _i, _P]),
 }

@@ -67,6 +67,7 @@ struct CompositeParams {
   float *g_sh_peer[8];
   int n_peers;
   float *g_sh_mc;
+  uint8_t *touched;  // optional: 1 for every Gaussian whose gradient rows this launch wrote
 };
 
 // ---------------------------------------------------------------- small device helpers
@@ -484,6 +485,7 @@ __device__ __forceinline__ void flush_batch(const CompositeParams &p, float *s_a
     }
     if (s.x == 0.f && s.y == 0.f && s.z == 0.f && s.w == 0.f) continue;
     const size_t g = (size_t)s_ids_b[j];
+    if (p.touched) p.touched[g] = 1;
     const float sv4[4] = {s.x, s.y, s.z, s.w};
     const int r0 = 4 * q;
     if (CC % 4 == 0 && p.gsh_vec && r0 + 3 < SHF) {
@@ -855,7 +857,7 @@ int gs3d_composite_sh_backward_peers(uint32_t M, const float *records, const flo
                                float pixel_size_x, float pixel_size_y, uint32_t H, uint32_t W,
                                uint32_t C, float thresh, int exact_decisions,
                                const uint64_t *peer_grad_sh_host, int n_peers,
-                               void *multicast_grad_sh, void *stream) {
+                               void *multicast_grad_sh, uint8_t *touched, void *stream) {
   (void)M;
   GS3D_REQUIRE(tile_size == TILE, GS3D_EUNSUPPORTED,
                "compositing kernels support tile_size 16 only (got %u)", tile_size);
@@ -876,6 +878,7 @@ int gs3d_composite_sh_backward_peers(uint32_t M, const float *records, const flo
   p.out_saved = out; p.grad_out = grad_out;
   p.g_mean = grad_mean2d; p.g_cov = grad_cov2d; p.g_sh = grad_sh; p.g_alpha = grad_alpha;
   p.gsh_sg = gsh_stride_g; p.gsh_sc = gsh_stride_c;
+  p.touched = touched;
   const uint32_t CC = C * C;
   p.sh_vec = (CC % 4 == 0) && (sh_stride_g % 4 == 0) && (sh_stride_c % 4 == 0) && aligned16(sh_coeffs);
   p.gsh_vec = (CC % 4 == 0) && (gsh_stride_g % 4 == 0) && (gsh_stride_c % 4 == 0) && aligned16(grad_sh);
@@ -912,7 +915,7 @@ int gs3d_composite_sh_backward(uint32_t M, const float *records, const float *sh
                                           gaussian_ids, out, grad_out, grad_mean2d, grad_cov2d, grad_sh,
                                           gsh_stride_g, gsh_stride_c, grad_alpha, topleft, c2w, tile_size,
                                           n_tiles_h, n_tiles_w, pixel_size_x, pixel_size_y, H, W, C,
-                                          thresh, exact_decisions, nullptr, 0, nullptr, stream);
+                                          thresh, exact_decisions, nullptr, 0, nullptr, nullptr, stream);
 }
 
 }  // extern "C"

@@ -473,6 +473,20 @@ project_backward_kernel(uint32_t N, const uint8_t *__restrict__ mask,
   bool keep = mask ? mask[i] != 0 : true;
   LeafGrad g;
   float ga = 0.0f;
+  float2 gm = make_float2(0.f, 0.f);
+  float4 gc = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (keep) {
+    // A view touches a small fraction of the Gaussians (cfg 2: ~2 %): when every upstream gradient of
+    // this Gaussian is zero the chain rule gives zeros -- skip the parameter loads and the arithmetic
+    // (and, when accumulating, the read-modify-write).  NaN/Inf upstream values compare unequal to 0.
+    gm = reinterpret_cast<const float2 *>(gm2d)[i];
+    gc = reinterpret_cast<const float4 *>(gcov)[i];
+    const float ga_up = galpha ? galpha[i] : 0.0f;
+    const float gd_up = gdepth ? gdepth[i] : 0.0f;
+    if (gm.x == 0.f && gm.y == 0.f && gc.x == 0.f && gc.y == 0.f && gc.z == 0.f && gc.w == 0.f &&
+        ga_up == 0.f && gd_up == 0.f)
+      keep = false;
+  }
   if (keep) {
     float p[3] = {mean[3 * (size_t)i], mean[3 * (size_t)i + 1], mean[3 * (size_t)i + 2]};
     float4 q4 = reinterpret_cast<const float4 *>(qvec)[i];
@@ -480,8 +494,6 @@ project_backward_kernel(uint32_t N, const uint8_t *__restrict__ mask,
     float s[3] = {act_exp(svec_param[3 * (size_t)i], svec_act),
                   act_exp(svec_param[3 * (size_t)i + 1], svec_act),
                   act_exp(svec_param[3 * (size_t)i + 2], svec_act)};
-    float2 gm = reinterpret_cast<const float2 *>(gm2d)[i];
-    float4 gc = reinterpret_cast<const float4 *>(gcov)[i];
     float gm2[2] = {gm.x, gm.y};
     float gS[4] = {gc.x, gc.y, gc.z, gc.w};
     project_backward_one(p, q, s, c2w, gm2, gS, gdepth ? gdepth[i] : 0.0f, detach, g);

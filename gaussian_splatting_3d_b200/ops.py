@@ -11,6 +11,7 @@ from . import capi
 from .capi import check, ptr
 
 _F32, _I32, _BOOL, _U8, _I64 = torch.float32, torch.int32, torch.bool, torch.uint8, torch.int64
+_I64P_t = C.POINTER(C.c_int64)
 
 
 def _chk(t, name, dtype):
@@ -212,9 +213,12 @@ def composite_sh_forward(records, sh, start, end, gaussian_ids, out, topleft, c2
 def composite_sh_backward(records, sh, start, end, gaussian_ids, out, grad_out, grad_mean, grad_cov,
                           grad_sh, grad_alpha, topleft, c2w, tile_size, n_tiles_h, n_tiles_w,
                           pixel_size_x, pixel_size_y, H, W, C_, thresh, exact=True, peer_ptrs=None,
-                          multicast_ptr=None):
+                          multicast_ptr=None, touched=None):
     """peer_ptrs: device addresses of every rank's grad_sh buffer (this rank included) for the fused
-    gradient exchange; multicast_ptr: NVSwitch multicast address of the same buffers (optional)."""
+    gradient exchange; multicast_ptr: NVSwitch multicast address of the same buffers (optional);
+    touched: uint8 [M], receives 1 for every Gaussian whose gradient rows were written (sparse exchange)."""
+    if touched is not None:
+        _chk(touched, "touched", _U8)
     _chk(records, "records", _F32)
     for t, n in ((start, "start"), (end, "end"), (gaussian_ids, "gaussian_ids")):
         _chk(t, n, _I32)
@@ -232,7 +236,7 @@ def composite_sh_backward(records, sh, start, end, gaussian_ids, out, grad_out, 
         ptr(grad_alpha), ptr(topleft), ptr(c2w), int(tile_size), int(n_tiles_h), int(n_tiles_w),
         float(pixel_size_x), float(pixel_size_y), int(H), int(W), int(C_), float(thresh),
         1 if exact else 0, C.cast(arr, C.c_void_p), n_peers,
-        C.c_void_p(int(multicast_ptr)) if multicast_ptr else None, _stream(out)),
+        C.c_void_p(int(multicast_ptr)) if multicast_ptr else None, ptr(touched), _stream(out)),
         "tile_based_vol_rendering_backward_sh")
 
 
@@ -260,3 +264,120 @@ def project_backward_fused(mask, mean, qvec, svec_param, alpha_param, svec_act, 
         ptr(gm), ptr(gq), ptr(gs), ptr(ga), ptr(grad_mean_acc), int(adc_mode), 1 if accumulate else 0,
         _stream(mean)), "project_backward_fused")
     return gm, gq, gs, ga
+
+
+# ---------------------------------------------------------------- sparse gradient exchange
+def _rows_args(blocks):
+    n = len(blocks)
+    for b in blocks:
+        _chk(b, "block", _F32)
+    ptrs = (C.c_uint64 * n)(*[b.data_ptr() for b in blocks])
+    widths = (C.c_uint32 * n)(*[b.numel() // b.size(0) for b in blocks])
+    return n, ptrs, widths
+
+
+def rows_gather(blocks, row_idx, packed):
+    """packed[u, :] = concat_s blocks[s][row_idx[u]].flatten()  (blocks: [N, ...] contiguous FP32)."""
+    _chk(row_idx, "row_idx", _I32)
+    _chk(packed, "packed", _F32)
+    n, ptrs, widths = _rows_args(blocks)
+    check(capi.lib.gs3d_rows_gather(n, C.cast(ptrs, C.c_void_p), C.cast(widths, C.c_void_p), ptr(row_idx),
+                                    row_idx.numel(), ptr(packed), packed.size(1), _stream(packed)), "rows_gather")
+    return packed
+
+
+def rows_scatter(blocks, row_idx, packed):
+    """blocks[s][row_idx[u]] = the matching columns of packed[u, :]."""
+    _chk(row_idx, "row_idx", _I32)
+    _chk(packed, "packed", _F32)
+    n, ptrs, widths = _rows_args(blocks)
+    check(capi.lib.gs3d_rows_scatter(n, C.cast(ptrs, C.c_void_p), C.cast(widths, C.c_void_p), ptr(row_idx),
+                                     row_idx.numel(), ptr(packed), packed.size(1), _stream(packed)), "rows_scatter")
+
+
+def rows_push_marked(marks, blocks, dst_offsets, peer_result_ptrs, peer_union_ptrs, multicast_ptr=None):
+    """Add the marked rows of the private `blocks` into every rank's result buffer (symmetric memory;
+    see gs3d_rows_push_marked).  dst_offsets: float offset of each block inside the result buffer."""
+    _chk(marks, "marks", _U8)
+    n, ptrs, widths = _rows_args(blocks)
+    offs = (C.c_uint64 * n)(*[int(o) for o in dst_offsets])
+    npeer = len(peer_result_ptrs)
+    res = (C.c_uint64 * npeer)(*[int(x) for x in peer_result_ptrs])
+    uni = (C.c_uint64 * npeer)(*[int(x) for x in peer_union_ptrs]) if peer_union_ptrs else None
+    check(capi.lib.gs3d_rows_push_marked(
+        ptr(marks), marks.numel(), n, C.cast(ptrs, C.c_void_p), C.cast(widths, C.c_void_p),
+        C.cast(offs, C.c_void_p), C.cast(res, C.c_void_p), C.cast(uni, C.c_void_p) if uni is not None else None,
+        npeer, C.c_void_p(int(multicast_ptr)) if multicast_ptr else None, _stream(marks)), "rows_push_marked")
+
+
+def rows_zero_marked(marks, blocks, clear_marks=True):
+    """Zero the rows of every marked Gaussian in `blocks` (may be empty), then clear the marks."""
+    _chk(marks, "marks", _U8)
+    if blocks:
+        n, ptrs, widths = _rows_args(blocks)
+        a, b = C.cast(ptrs, C.c_void_p), C.cast(widths, C.c_void_p)
+    else:
+        n, a, b = 0, None, None
+    check(capi.lib.gs3d_rows_zero_marked(ptr(marks), marks.numel(), n, a, b, 1 if clear_marks else 0,
+                                         _stream(marks)), "rows_zero_marked")
+
+
+def marks_broadcast(marks, peer_union_ptrs):
+    """Set byte g of every rank's union marks for each g with marks[g] != 0."""
+    _chk(marks, "marks", _U8)
+    n = len(peer_union_ptrs)
+    uni = (C.c_uint64 * n)(*[int(x) for x in peer_union_ptrs])
+    check(capi.lib.gs3d_marks_broadcast(ptr(marks), marks.numel(), C.cast(uni, C.c_void_p), n, _stream(marks)),
+          "marks_broadcast")
+
+
+def rows_pull_marked(union_marks, widths, offsets, peer_private_ptrs, peer_result_ptrs, rank,
+                     multicast_private=None, multicast_result=None):
+    """Sparse NVLS all-reduce of the union-marked rows (see gs3d_rows_pull_marked)."""
+    _chk(union_marks, "union_marks", _U8)
+    n, npeer = len(widths), len(peer_private_ptrs)
+    w = (C.c_uint32 * n)(*[int(x) for x in widths])
+    o = (C.c_uint64 * n)(*[int(x) for x in offsets])
+    src = (C.c_uint64 * npeer)(*[int(x) for x in peer_private_ptrs])
+    dst = (C.c_uint64 * npeer)(*[int(x) for x in peer_result_ptrs])
+    check(capi.lib.gs3d_rows_pull_marked(
+        ptr(union_marks), union_marks.numel(), n, C.cast(w, C.c_void_p), C.cast(o, C.c_void_p),
+        C.cast(src, C.c_void_p), C.cast(dst, C.c_void_p), npeer, int(rank),
+        C.c_void_p(int(multicast_private)) if multicast_private else None,
+        C.c_void_p(int(multicast_result)) if multicast_result else None, _stream(union_marks)), "rows_pull_marked")
+
+
+# ---------------------------------------------------------------- tile-row bands (tile-sharded render)
+def row_duplicate_counts(aabb_topleft, aabb_bottomright, n_tiles_h):
+    """Duplicates per tile row, int64 [n_tiles_h] (device)."""
+    _chk(aabb_topleft, "aabb_topleft", _I32)
+    _chk(aabb_bottomright, "aabb_bottomright", _I32)
+    dev = aabb_topleft.device
+    out = torch.empty(int(n_tiles_h), dtype=_I64, device=dev)
+    scratch = _scratch(8 * (int(n_tiles_h) + 1), dev)
+    check(capi.lib.gs3d_row_duplicate_counts(aabb_topleft.size(0), ptr(aabb_topleft), ptr(aabb_bottomright),
+                                             int(n_tiles_h), ptr(out), ptr(scratch), scratch.numel(),
+                                             _stream(aabb_topleft)), "row_duplicate_counts")
+    return out
+
+
+def clip_rects_to_rows(aabb_topleft, aabb_bottomright, depth, row_begin, row_end):
+    """-> (tl [M',2], br [M',2], depth [M',1], index int32 [M'], n_dub_band): the Gaussians whose rect
+    still covers a tile after clipping to tile rows [row_begin, row_end), in ascending index order."""
+    _chk(aabb_topleft, "aabb_topleft", _I32)
+    _chk(aabb_bottomright, "aabb_bottomright", _I32)
+    _chk(depth, "depth", _F32)
+    N = aabb_topleft.size(0)
+    dev = aabb_topleft.device
+    tl = torch.empty(N, 2, dtype=_I32, device=dev)
+    br = torch.empty(N, 2, dtype=_I32, device=dev)
+    dp = torch.empty(N, 1, dtype=_F32, device=dev)
+    idx = torch.empty(N, dtype=_I32, device=dev)
+    counts = (C.c_int64 * 2)(0, 0)
+    scratch = _scratch(capi.lib.gs3d_clip_scratch_bytes(N), dev)
+    check(capi.lib.gs3d_clip_rects_to_rows(N, ptr(aabb_topleft), ptr(aabb_bottomright), ptr(depth), int(row_begin),
+                                           int(row_end), ptr(tl), ptr(br), ptr(dp), ptr(idx),
+                                           C.cast(counts, _I64P_t), ptr(scratch), scratch.numel(),
+                                           _stream(depth)), "clip_rects_to_rows")
+    m = int(counts[0])
+    return tl[:m], br[:m], dp[:m], idx[:m], int(counts[1])

@@ -28,48 +28,113 @@ class FlatGradients:
     every rank maps every other rank's buffer (and the NVSwitch multicast address when available),
     and the compositing-backward kernel reduces its SH gradient rows into ALL ranks' buffers while it
     runs (gs3d_composite_sh_backward_peers).  exchange() then only all-reduces the small dense block.
+
+    push=True (symmetric memory as well): the backward kernels accumulate into a PRIVATE buffer and mark
+    the Gaussians they touch; exchange() launches one kernel that adds each marked row -- once, already
+    summed over this rank's tiles and views -- into the RESULT buffer (the one `.grad` aliases) of every
+    rank through the NVSwitch multicast address (multimem.red) or peer by peer, and sets the row's byte
+    in every rank's union marks; only marked rows are ever cleared.  Two result buffers alternate, so ONE
+    cross-rank barrier per step orders everything.  No NCCL call, no host round trip, U_own * 240 B leave
+    each GPU per step (gs3d_rows_push_marked / gs3d_rows_zero_marked).  After exchange(), `.flat`,
+    `.views` and the parameters' `.grad` refer to the buffer that holds this step's sum.
+
+    pull=True: same buffers and marks, but the sum is formed INSIDE the NVSwitch: the ranks OR their marks
+    into every rank's union marks, and each rank then reads the sum over all ranks of every n-th chunk
+    of union rows with multimem.ld_reduce and broadcasts it with multimem.st (gs3d_marks_broadcast /
+    gs3d_rows_pull_marked): each GPU ingests ~(1 + 1/n) * U rows instead of n * U -- the form that
+    scales to 8 ranks, where the push form is bound by the NVLink packet rate of 16-byte reductions.
+
+    sparse=True: the compositing backward marks the Gaussians whose gradient rows it writes; exchange()
+    ORs the marks over the ranks (3 MB all-reduce), packs the union rows of all five blocks into one
+    [U, 60] matrix (gs3d_rows_gather), all-reduces that -- U * 240 B instead of N * 236 B -- and
+    unpacks the sum (gs3d_rows_scatter).  Untouched rows are zero on every rank and stay zero.
     """
 
     ORDER = ("sh_coeffs", "mean", "qvec", "svec_before_activation", "alpha_before_activation")
 
-    def __init__(self, module, fused=False, group=None, use_multicast=True):
+    def __init__(self, module, fused=False, group=None, use_multicast=True, sparse=False, push=False, pull=False):
         self.names = list(self.ORDER)
         self.params = [getattr(module, n) for n in self.names]
         total = sum(p.numel() for p in self.params)
         dev = self.params[0].device
+        N = self.params[0].size(0)
         self.group = group
-        self.fused = bool(fused) and dist.is_initialized() and dist.get_world_size(group) > 1
+        multi = dist.is_initialized() and dist.get_world_size(group) > 1
+        self.pull = bool(pull) and multi              # pull implies the push bookkeeping (marks, two result buffers)
+        self.push = (bool(push) or self.pull) and multi
+        self.fused = bool(fused) and multi and not self.push
+        self.sparse = bool(sparse) and not self.fused and not self.push
+        self.touched = torch.zeros(N, dtype=torch.uint8, device=dev) if (self.sparse or self.push) else None
+        self.last_union_rows = None
         self.handle = None
-        if self.fused:
-            import torch.distributed._symmetric_memory as symm_mem
+        self.local = self.local_views = self.union = self.union_handle = None
+        def carve(buf):
+            views, offsets, off = [], [], 0
+            for p in self.params:
+                views.append(buf[off:off + p.numel()].view_as(p))
+                offsets.append(off)
+                off += p.numel()
+            return views, offsets
 
-            self.flat = symm_mem.empty(total, dtype=torch.float32, device=dev)
-            self.handle = symm_mem.rendezvous(self.flat, group if group is not None else dist.group.WORLD)
-        else:
-            self.flat = torch.empty(total, dtype=torch.float32, device=dev)
-        self.flat.zero_()
-        self.views = []
-        off = 0
-        for p in self.params:
-            v = self.flat[off:off + p.numel()].view_as(p)
-            p.grad = v
-            self.views.append(v)
-            off += p.numel()
-        self.n_sh = self.params[0].numel()
         self.peer_ptrs = None
         self.multicast_ptr = None
-        if self.fused:
+        self._res = None
+        if self.fused or self.push:
+            import torch.distributed._symmetric_memory as symm_mem
+
+            grp = group if group is not None else dist.group.WORLD
+
+            def symmetric(n, dtype):
+                t = symm_mem.empty(n, dtype=dtype, device=dev)
+                h = symm_mem.rendezvous(t, grp)
+                t.zero_()
+                return t, h
+
+            self.flat, self.handle = symmetric(total, torch.float32)
+            if self.push:
+                # two result buffers used alternately: the one for step k+1 is reset during step k, so the
+                # barrier that ends step k's exchange also orders "reset" before "peers push into it"
+                self._res = []
+                for b in range(2):
+                    buf, h = (self.flat, self.handle) if b == 0 else symmetric(total, torch.float32)
+                    uni, uh = symmetric(N, torch.uint8)
+                    mc = int(h.multicast_ptr) if use_multicast else 0
+                    self._res.append(dict(flat=buf, handle=h, views=carve(buf)[0], union=uni,
+                                          peer_ptrs=[int(p) for p in h.buffer_ptrs],
+                                          union_ptrs=[int(p) for p in uh.buffer_ptrs], multicast=mc if mc else None))
+                self._cur = 0
+                self.union = self._res[0]["union"]
+                if self.pull:  # peers read this rank's private rows: symmetric (multicast-mapped) as well
+                    self.local, lh = symmetric(total, torch.float32)
+                    lmc = int(lh.multicast_ptr) if use_multicast else 0
+                    self._local_peer_ptrs = [int(p) for p in lh.buffer_ptrs]
+                    self._local_multicast = lmc if lmc else None
+                    self._rank = dist.get_rank(grp)
+                else:
+                    self.local = torch.zeros(total, dtype=torch.float32, device=dev)
+        else:
+            self.flat = torch.zeros(total, dtype=torch.float32, device=dev)
+        self.views, self.offsets = carve(self.flat)
+        for p, v in zip(self.params, self.views):
+            p.grad = v
+        if self.local is not None:
+            self.local_views = carve(self.local)[0]
+        self.n_sh = self.params[0].numel()
+        if self.fused or self.push:
             # the SH block starts at offset 0 of the symmetric buffer on every rank
             self.peer_ptrs = [int(p) for p in self.handle.buffer_ptrs]
             mc = int(self.handle.multicast_ptr) if use_multicast else 0
             self.multicast_ptr = mc if mc else None
         self.module = None
+        self._dirty = False
 
     def attach(self, renderer):
-        bufs = dict(zip(self.names, self.views))
+        bufs = dict(zip(self.names, self.local_views if self.push else self.views))
         if self.fused:
             bufs["sh_peer_ptrs"] = self.peer_ptrs
             bufs["sh_multicast_ptr"] = self.multicast_ptr
+        if self.touched is not None:
+            bufs["touched"] = self.touched
         renderer.grad_buffers = bufs
         self.module = renderer
         return self
@@ -86,7 +151,18 @@ class FlatGradients:
             dist.barrier(group=self.group)
 
     def zero(self):
-        self.flat.zero_()
+        if self.push and self.module is not None:
+            from . import ops
+
+            # this rank's private rows written last step (own marks); the result buffer of this step was
+            # already reset during the previous step's exchange()
+            ops.rows_zero_marked(self.touched, self.local_views, clear_marks=True)
+            cur = self._res[self._cur]
+            self.flat, self.views, self.union = cur["flat"], cur["views"], cur["union"]
+        else:
+            self.flat.zero_()
+            if self.touched is not None:
+                self.touched.zero_()
         for p, v in zip(self.params, self.views):
             p.grad = v  # optimisers / zero_grad(set_to_none) may have dropped the alias
         if self.fused:
@@ -106,14 +182,54 @@ class FlatGradients:
         if self.fused and self.module is not None:
             self._barrier()  # every rank's in-kernel reductions into this buffer have landed
             dist.all_reduce(self.flat[self.n_sh:], op=dist.ReduceOp.SUM, group=self.group)
+        elif self.push and self.module is not None:
+            from . import ops
+
+            cur, nxt = self._res[self._cur], self._res[self._cur ^ 1]
+            if self.pull:
+                ops.marks_broadcast(self.touched, cur["union_ptrs"])
+                cur["handle"].barrier(channel=0)  # union marks complete, every rank's private rows final
+                widths = [v.numel() // v.size(0) for v in self.views]
+                ops.rows_pull_marked(cur["union"], widths, self.offsets, self._local_peer_ptrs, cur["peer_ptrs"],
+                                     self._rank, self._local_multicast, cur["multicast"])
+            else:
+                ops.rows_push_marked(self.touched, self.local_views, self.offsets, cur["peer_ptrs"],
+                                     cur["union_ptrs"], cur["multicast"])
+            # reset the other result buffer (rows any rank pushed into two steps ago) for the next step
+            ops.rows_zero_marked(nxt["union"], nxt["views"], clear_marks=True)
+            cur["handle"].barrier(channel=0)  # every rank's rows have landed; every 'next' buffer is clean
+            self._cur ^= 1
+        elif self.sparse and self.module is not None:
+            self._exchange_sparse()
         else:
             dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=self.group)
         if average:
             self.flat.div_(dist.get_world_size(self.group))
         return self.flat
 
+    def _exchange_sparse(self):
+        from . import ops
+
+        marks = self.touched
+        dist.all_reduce(marks, op=dist.ReduceOp.MAX, group=self.group)   # OR of the ranks' marks
+        idx = union_rows(marks)                                           # same list on every rank
+        self.last_union_rows = int(idx.numel())
+        if idx.numel() == 0:
+            return
+        width = sum(v.numel() // v.size(0) for v in self.views)
+        packed = torch.empty(idx.numel(), (width + 3) // 4 * 4, dtype=torch.float32, device=self.flat.device)
+        ops.rows_gather(self.views, idx, packed)
+        dist.all_reduce(packed, op=dist.ReduceOp.SUM, group=self.group)
+        ops.rows_scatter(self.views, idx, packed)
+
     def all_reduce(self, group=None, average=False):
         return self.exchange(average=average)
+
+
+def union_rows(marks):
+    """int32 indices of the non-zero entries of the (already OR-reduced) per-Gaussian marks, ascending;
+    identical on every rank because the marks are."""
+    return torch.nonzero(marks, as_tuple=False).view(-1).to(torch.int32)
 
 
 def shard_views(n_views, rank, world):
@@ -168,8 +284,13 @@ def sync_adc(renderer, group=None):
 
 
 def row_duplicate_counts(aabb_topleft, aabb_bottomright, n_tiles_h):
-    """Duplicates per tile row from the per-Gaussian rects (int64 [n_tiles_h]); difference array +
-    prefix sum, integer arithmetic only, so every rank computes the same numbers."""
+    """Duplicates per tile row from the per-Gaussian rects (int64 [n_tiles_h]); integer arithmetic only,
+    so every rank computes the same numbers.  CUDA tensors: gs3d_row_duplicate_counts (per-block
+    difference arrays); CPU tensors (host-logic tests): the same difference array in torch."""
+    if aabb_topleft.is_cuda:
+        from . import ops
+
+        return ops.row_duplicate_counts(aabb_topleft, aabb_bottomright, n_tiles_h)
     tl, br = aabb_topleft.long(), aabb_bottomright.long()
     w = (br[:, 0] - tl[:, 0] + 1).clamp_(min=0)
     valid = (br[:, 1] >= tl[:, 1]) & (w > 0)
@@ -228,12 +349,15 @@ def render_band(renderer, c2w, camera_info, row_begin=None, row_end=None, k1=Non
     ntw = W // tile + (W % tile > 0)
     if row_begin is None:
         row_begin, row_end = 0, nth
-    tl, br, n_band = clip_rects_to_band(k1["tl"], k1["br"], row_begin, row_end)
-    n_band = int(n_band.item())
+    # clip to the band and keep only the Gaussians that still cover a tile: the band's depth sort and
+    # emission then run over ~N/world Gaussians; ids come back as original indices through `index`
+    tl, br, depth_b, index, n_band = ops.clip_rects_to_rows(k1["tl"], k1["br"], k1["depth"], row_begin, row_end)
     ids = torch.empty(n_band, dtype=torch.int32, device=dev)
     start = torch.empty(nth * ntw, dtype=torch.int32, device=dev)
     end = torch.empty(nth * ntw, dtype=torch.int32, device=dev)
-    ops.tile_culling_aabb_start_end(tl, br, ids, start, end, k1["depth"], nth, ntw, check_count=False)
+    ops.tile_culling_aabb_start_end(tl, br, ids, start, end, depth_b, nth, ntw, check_count=False)
+    if n_band:
+        ids = torch.index_select(index, 0, ids)
     out = torch.zeros(H * W * 3, dtype=torch.float32, device=dev)
     topleft = torch.tensor([-cam.cx / cam.fx, -cam.cy / cam.fy], dtype=torch.float32).to(dev)
     bg = renderer.bg_rgb if renderer.bg else None

@@ -184,7 +184,48 @@ int gs3d_composite_sh_backward_peers(uint32_t M, const float *records, const flo
                                      float pixel_size_x, float pixel_size_y, uint32_t H, uint32_t W,
                                      uint32_t C, float thresh, int exact_decisions,
                                      const uint64_t *peer_grad_sh_host, int n_peers,
-                                     void *multicast_grad_sh, void *stream);
+                                     void *multicast_grad_sh, uint8_t *touched, void *stream);
+
+/* ---- sparse gradient exchange (view-sharded training, new capability).  `touched` above (may be
+ * NULL) receives a 1 for every Gaussian whose gradient rows the backward wrote; after the ranks have
+ * OR-ed their marks, only the union rows are all-reduced.  gs3d_rows_gather packs rows row_idx[0..U)
+ * of n_blocks row-major blocks (block s = [N, block_widths_host[s]] floats at device address
+ * block_ptrs_host[s]; both arrays live on the HOST) side by side into packed [U, W] (W >= sum of the
+ * widths, padding columns zeroed); gs3d_rows_scatter writes a packed matrix back. */
+int gs3d_rows_gather(int n_blocks, const uint64_t *block_ptrs_host, const uint32_t *block_widths_host,
+                     const int32_t *row_idx, uint32_t U, float *packed, uint32_t W, void *stream);
+int gs3d_rows_scatter(int n_blocks, const uint64_t *block_ptrs_host, const uint32_t *block_widths_host,
+                      const int32_t *row_idx, uint32_t U, const float *packed, uint32_t W, void *stream);
+
+/* Push form of the sparse exchange over NVLink / NVSwitch symmetric memory (no NCCL, no host round
+ * trip): for every Gaussian g with marks[g] != 0, the row g of each private block s ([N, width_s] at
+ * src_ptrs_host[s]) is ADDED into every rank's result buffer at float offset dst_offsets_host[s] +
+ * g*width_s -- with multimem.red.add on multicast_result when it is not NULL, else with one
+ * red.global.add per entry of peer_result_ptrs_host[0..n_peers) (this rank included) -- and
+ * union marks byte g is set on every rank (peer_union_ptrs_host, may be NULL).  The result buffers must
+ * be zero in those rows and a cross-rank barrier passed before the launch; after a second barrier
+ * every result buffer holds the sum over ranks.  gs3d_rows_zero_marked clears the marked rows of the
+ * given blocks (and, clear_marks != 0, the marks): the per-step reset of both buffers. */
+int gs3d_rows_push_marked(const uint8_t *marks, uint32_t N, int n_blocks, const uint64_t *src_ptrs_host,
+                          const uint32_t *block_widths_host, const uint64_t *dst_offsets_host,
+                          const uint64_t *peer_result_ptrs_host, const uint64_t *peer_union_ptrs_host,
+                          int n_peers, void *multicast_result, void *stream);
+int gs3d_rows_zero_marked(uint8_t *marks, uint32_t N, int n_blocks, const uint64_t *block_ptrs_host,
+                          const uint32_t *block_widths_host, int clear_marks, void *stream);
+
+/* Pull form (a sparse NVLS all-reduce; what scales to 8 ranks): gs3d_marks_broadcast sets byte g in
+ * every rank's union marks for each marked g; after a cross-rank barrier, gs3d_rows_pull_marked on rank
+ * `rank` walks every n_peers-th 512-row chunk of its union marks and, per marked row, reads the sum of
+ * ALL ranks' private rows (multimem.ld_reduce.add on multicast_private: reduced inside the NVSwitch;
+ * without multicast, peer loads) and stores it into ALL ranks' result buffers (multimem.st on
+ * multicast_result; else peer stores).  Private and result buffers share one layout: block s of width
+ * block_widths_host[s] starts at float offset block_offsets_host[s].  A second barrier completes it. */
+int gs3d_marks_broadcast(const uint8_t *marks, uint32_t N, const uint64_t *peer_union_ptrs_host, int n_peers,
+                         void *stream);
+int gs3d_rows_pull_marked(uint8_t *union_marks, uint32_t N, int n_blocks, const uint32_t *block_widths_host,
+                          const uint64_t *block_offsets_host, const uint64_t *peer_private_ptrs_host,
+                          const uint64_t *peer_result_ptrs_host, int n_peers, int rank,
+                          const void *multicast_private, void *multicast_result, void *stream);
 
 /* ---- a9 + a10 fused: chain rule from (grad_mean2d, grad_cov2d, grad_alpha) to the leaf
  * parameters through projection (Q6) and the activations (sh_renderer.py:318-324), for the
@@ -202,6 +243,24 @@ int gs3d_project_backward_fused(uint32_t N, const uint8_t *mask, const float *me
                                 float *grad_mean, float *grad_qvec, float *grad_svec_param,
                                 float *grad_alpha_param, float *grad_mean_acc, int adc_mode,
                                 int accumulate, void *stream);
+
+/* ---- tile-sharded render (new capability, SURVEY.md 8e / cfg 5): tiles are independent after
+ * projection, so rank r bins and composites the tile rows [row_begin, row_end) of its band only.
+ * gs3d_row_duplicate_counts: duplicates per tile row, row_counts int64 [n_tiles_h] (device), from the
+ * rects of gs/culling.py:22-31 -- what the bands are balanced by (scratch >= 8*(n_tiles_h+1) bytes).
+ * gs3d_clip_rects_to_rows: clips every rect to the band and compacts the Gaussians that still cover a
+ * tile, in ascending index order (deterministic): tl_out/br_out [M',2], depth_out [M'], index_out [M']
+ * (original index), all caller-allocated for N entries; counts_host[0] = M', counts_host[1] = the
+ * band's duplicate count.  The band is then binned over M' Gaussians (gs3d_tile_culling_aabb_start_end)
+ * and the resulting gaussian_ids are mapped back through index_out. */
+int gs3d_row_duplicate_counts(uint32_t N, const int32_t *aabb_topleft, const int32_t *aabb_bottomright,
+                              uint32_t n_tiles_h, int64_t *row_counts, void *scratch, size_t scratch_bytes,
+                              void *stream);
+size_t gs3d_clip_scratch_bytes(uint32_t N);
+int gs3d_clip_rects_to_rows(uint32_t N, const int32_t *aabb_topleft, const int32_t *aabb_bottomright,
+                            const float *depth, int row_begin, int row_end, int32_t *tl_out,
+                            int32_t *br_out, float *depth_out, int32_t *index_out, int64_t *counts_host,
+                            void *scratch, size_t scratch_bytes, void *stream);
 
 #ifdef __cplusplus
 }

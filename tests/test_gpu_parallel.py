@@ -163,3 +163,120 @@ def test_two_gpu_fused_gradient_exchange(use_multicast):
               f"rel_sh={rel_sh:.2e} rel_rest={rel_rest:.2e}")
         assert info[0] and info[2] == 2
         assert rel_sh < 1e-4 and rel_rest < 1e-4
+
+
+def _worker_sparse(rank, world, port, q, mode):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dev = f"cuda:{rank}"
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device(dev))
+    import math
+
+    from gaussian_splatting_3d_b200 import parallel as P
+
+    r, sc, cam = _renderer(dev, name="cfg2", n=80_000, C=4)
+    r.train()
+    c2ws = []
+    for i in range(4):
+        a = math.radians(3.0 * (i - 1.5))
+        c2ws.append(torch.tensor([[math.cos(a), 0, math.sin(a), 0], [0, 1, 0, 0], [-math.sin(a), 0, math.cos(a), 0]],
+                                 dtype=torch.float32, device=dev))
+    targets = [S.make_target(cam, i).to(dev) for i in range(4)]
+    flat = P.FlatGradients(r, sparse=(mode == "sparse"), push=(mode.startswith("push")),
+                           pull=(mode.startswith("pull")), use_multicast=not mode.endswith("-peer")).attach(r)
+    assert flat.sparse == (mode == "sparse") and flat.push == (mode != "sparse") and flat.pull == mode.startswith("pull")
+    for _ in range(3):  # repeatedly: marks and buffers must be reset correctly
+        P.view_sharded_step(r, flat, c2ws, cam, targets)
+    got = flat.flat.clone()
+    r2, _, _ = _renderer(dev, name="cfg2", n=80_000, C=4)
+    r2.train()
+    flat2 = P.FlatGradients(r2)
+    flat2.zero()
+    for i in range(4):
+        ((r2(c2ws[i], cam) - targets[i]) ** 2).mean().backward()
+    want = flat2.flat
+    rel = float((got - want).norm() / want.norm())
+    # rows outside the union must be exactly zero in the serial sum too (nothing was dropped)
+    N = r.mean.size(0)
+    nz_rows = int((want[: flat.n_sh].view(N, -1).abs().sum(1) > 0).sum())
+    union = flat.last_union_rows if mode == "sparse" else int(flat.union.count_nonzero())
+    q.put((rank, rel, union, nz_rows, N))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
+@pytest.mark.parametrize("mode", ["sparse", "push", "push-peer", "pull", "pull-peer"])
+def test_two_gpu_sparse_gradient_exchange(mode):
+    """Exchange of the touched rows only -- 'sparse': union marks + NCCL all-reduce of the packed rows
+    (gs3d_rows_gather / gs3d_rows_scatter); 'push': every rank adds its rows into every rank's result
+    buffer over the NVSwitch multicast address ('push-peer': peer by peer); 'pull': union marks, then
+    multimem.ld_reduce + multimem.st per union row ('pull-peer': peer loads / stores) -- == serial sum over the
+    four views; the union covers every non-zero row."""
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29900 + (os.getpid() % 2000) + {"sparse": 0, "push": 11, "push-peer": 23, "pull": 37, "pull-peer": 41}[mode]
+    procs = [ctx.Process(target=_worker_sparse, args=(r, 2, port, q, mode)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=300) for _ in range(2)]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for rank, rel, union_rows, nz_rows, N in res:
+        print(f"[{mode} dp rank {rank}] union rows {union_rows} of {N} (non-zero SH rows in the serial sum: {nz_rows}) "
+              f"rel={rel:.2e}")
+        assert rel < 1e-4
+        assert nz_rows <= union_rows < N
+
+
+@pytest.mark.gpu
+def test_rows_gather_scatter_roundtrip():
+    from gaussian_splatting_3d_b200 import ops
+
+    dev = "cuda:0"
+    g = torch.Generator().manual_seed(3)
+    N = 1000
+    blocks = [torch.randn(N, 3, 16, generator=g).to(dev), torch.randn(N, 3, generator=g).to(dev),
+              torch.randn(N, 4, generator=g).to(dev), torch.randn(N, generator=g).to(dev)]
+    idx = torch.randperm(N, generator=g)[:137].sort().values.int().to(dev)
+    packed = torch.full((137, 60), float("nan"), device=dev)
+    ops.rows_gather(blocks, idx, packed)
+    want = torch.cat([b.view(N, -1)[idx.long()] for b in blocks], 1)
+    assert torch.equal(packed[:, :56], want) and bool((packed[:, 56:] == 0).all())
+    outs = [torch.zeros_like(b) for b in blocks]
+    ops.rows_scatter(outs, idx, packed * 2)
+    for o, b in zip(outs, blocks):
+        ref = torch.zeros_like(b)
+        ref[idx.long()] = 2 * b[idx.long()]
+        assert torch.equal(o, ref)
+    # empty index list is a no-op
+    ops.rows_gather(blocks, idx[:0], packed[:0])
+
+
+def test_band_kernels_match_torch_restatement():
+    """gs3d_row_duplicate_counts / gs3d_clip_rects_to_rows against the integer torch restatement
+    (parallel.row_duplicate_counts on CPU tensors, parallel.clip_rects_to_band)."""
+    from gaussian_splatting_3d_b200 import ops
+    from gaussian_splatting_3d_b200 import parallel as P
+
+    g = torch.Generator().manual_seed(11)
+    N, nth, ntw = 20_000, 47, 63
+    tl = torch.stack([torch.randint(0, ntw, (N,), generator=g), torch.randint(0, nth, (N,), generator=g)], 1).int()
+    ext = torch.stack([torch.randint(-1, 6, (N,), generator=g), torch.randint(-1, 9, (N,), generator=g)], 1).int()
+    br = tl + ext                                      # some rects are empty (extent -1)
+    br[:, 0].clamp_(max=ntw - 1)
+    br[:, 1].clamp_(max=nth - 1)
+    depth = torch.rand(N, 1, generator=g)
+    want_rows = P.row_duplicate_counts(tl, br, nth)     # CPU restatement
+    got_rows = ops.row_duplicate_counts(tl.cuda(), br.cuda(), nth)
+    assert torch.equal(got_rows.cpu(), want_rows)
+    for r0, r1 in ((0, nth), (5, 17), (30, 31), (46, 47), (10, 10)):
+        ctl, cbr, n_want = P.clip_rects_to_band(tl, br, r0, r1)
+        keep = ((cbr[:, 0] - ctl[:, 0] + 1) > 0) & ((cbr[:, 1] - ctl[:, 1] + 1) > 0)
+        gtl, gbr, gd, gidx, n_got = ops.clip_rects_to_rows(tl.cuda(), br.cuda(), depth.cuda(), r0, r1)
+        assert n_got == int(n_want)
+        assert torch.equal(gidx.cpu().long(), torch.nonzero(keep).view(-1))
+        assert torch.equal(gtl.cpu(), ctl[keep]) and torch.equal(gbr.cpu(), cbr[keep])
+        assert torch.equal(gd.cpu(), depth[keep])

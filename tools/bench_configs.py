@@ -4,6 +4,8 @@ contract bench for cfg 2 / cfg 4):
 
   cfg3  500 k Gaussians, C=3, 1008x756: FULL training step = forward + L2 loss + backward +
         ADC position-grad accumulation (fused into the projection-backward kernel) + cnt + Adam.
+  cfg4  cfg-2 scene, 8 cameras on a ring per step, views sharded over the ranks, gradients exchanged
+        (argv[3]: push | fused | sparse | allreduce); strong scaling: T_G for the same 8-camera step.
   cfg5  6 M Gaussians, C=4, 3840x2160 forward; on N ranks (torchrun) tile rows are sharded.
 
   python tools/bench_configs.py cfg3
@@ -50,8 +52,9 @@ def main():
     torch.cuda.set_device(dev)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
-    cam = S.make_camera(which)
-    sc = S.make_scene(which, seed=0)
+    scene_name = "cfg2" if which == "cfg4" else which
+    cam = S.make_camera(scene_name)
+    sc = S.make_scene(scene_name, seed=0)
     C = sc["C"]
     r = S.renderer_from_scene(sc, S.make_cfg(device=str(dev), sh_order=C))
     c2w = sc["c2w"].to(dev)
@@ -75,6 +78,22 @@ def main():
         ms = timed(step, steps, world, dev)
         out.update({"metric": "full training steps/s (fwd + L2 + bwd + ADC accumulation + Adam)",
                     "ms_per_step": ms, "value": 1000.0 / ms, "n_dub": r.total_dub_gaussians})
+    elif which == "cfg4":
+        mode = sys.argv[3] if len(sys.argv) > 3 else "push"
+        r.train()
+        c2ws = [c.to(dev) for c in S.ring_cameras(8)]
+        targets = [S.make_target(cam, i).to(dev) for i in range(8)]
+        flat = P.FlatGradients(r, fused=(mode == "fused"), sparse=(mode == "sparse"), push=(mode == "push")).attach(r)
+
+        def step():
+            P.view_sharded_step(r, flat, c2ws, cam, targets)
+
+        for _ in range(3):
+            step()
+        ms = timed(step, steps, world, dev)
+        out.update({"metric": "8-camera training steps/s (views sharded, gradients exchanged, ADC statistics synced)",
+                    "exchange": mode if world > 1 else None, "ms_per_step": ms, "value": 1000.0 / ms,
+                    "views_per_s": 8000.0 / ms})
     else:
         r.eval()
 
