@@ -24,13 +24,24 @@ class Camera(C.Structure):
     ]
 
 
+class AdamSegment(C.Structure):
+    """struct gs3d_adam_segment: one parameter tensor of the optimiser step."""
+
+    _fields_ = [
+        ("param", C.c_void_p), ("grad", C.c_void_p), ("exp_avg", C.c_void_p), ("exp_avg_sq", C.c_void_p),
+        ("n", C.c_uint64), ("lr", C.c_double),
+    ]
+
+
 _P = C.c_void_p
 _u32 = C.c_uint32
 _f = C.c_float
+_d = C.c_double
 _i = C.c_int
 _sz = C.c_size_t
 _CAM = C.POINTER(Camera)
 _I64P = C.POINTER(C.c_int64)
+_ADAM = C.POINTER(AdamSegment)
 
 # name -> (restype, argtypes); must list every symbol of include/gs3d_b200.h (tests check this)
 SIGNATURES = {
@@ -68,6 +79,13 @@ SIGNATURES = {
     "gs3d_rows_pull_marked": (_i, [_P, _u32, _i, _P, _P, _P, _P, _i, _i, _P, _P, _P]),
     "gs3d_project_backward_fused": (_i, [_u32, _P, _P, _P, _P, _P, _i, _i, _P, _i, _P, _P, _P, _P, _P,
                                          _P, _P, _P, _i, _i, _P]),
+    "gs3d_set_stage_counters": (_i, [_P]),
+    "gs3d_adam_step": (_i, [_i, _ADAM, _d, _d, _d, _u32, _i, _P]),
+    "gs3d_adc_classify": (_i, [_u32, _P, _P, _i, _f, _P, _i, _f, _P, _P]),
+    "gs3d_adc_classify_alpha": (_i, [_u32, _P, _i, _f, _P, _P]),
+    "gs3d_adc_scratch_bytes": (_sz, [_u32]),
+    "gs3d_adc_plan": (_i, [_u32, _P, _i, _I64P, _P, _sz, _P]),
+    "gs3d_adc_apply": (_i, [_u32, _P, _i, _P, _I64P, _P, _P, _P, _P, _P, _u32, _i, _f, _P, _P, _P, _P, _P, _P, _P]),
 }
 
 

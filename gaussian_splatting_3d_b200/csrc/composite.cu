@@ -68,6 +68,7 @@ struct CompositeParams {
   int n_peers;
   float *g_sh_mc;
   uint8_t *touched;  // optional: 1 for every Gaussian whose gradient rows this launch wrote
+  unsigned long long *stats;  // optional (gs3d_set_stage_counters): [0] += staged duplicates (fwd), [1] (bwd)
 };
 
 // ---------------------------------------------------------------- small device helpers
@@ -404,7 +405,8 @@ composite_fwd_kernel(const CompositeParams p) {
   if (id_lane) s_ids[B + threadIdx.x] = my_id;
   my_id = (id_lane && 2 * B + threadIdx.x < n_this) ? ids[2 * B + threadIdx.x] : 0;
 
-  for (int cb = 0; cb < n_batches; ++cb) {
+  int cb = 0;
+  for (; cb < n_batches; ++cb) {
     cp_async_wait<0>();
     if (__syncthreads_and(dead != 0.0f)) break;  // all pixels of the tile finished -> stop staging
     const int buf = cb & 1;
@@ -449,6 +451,8 @@ composite_fwd_kernel(const CompositeParams p) {
     }
   }
   cp_async_wait<0>();
+  // batches 0..cb have been staged when the loop ends at cb (all of them when it ran to completion)
+  if (p.stats && threadIdx.x == 0) atomicAdd(p.stats, (unsigned long long)min(n_this, (cb + 1) * B));
   if (!inside) return;
   if (p.bg && T > p.thresh) {  // vol_render_bg.h:90-94
     o0 = o0 * T + p.bg[0] * (1.0f - T);
@@ -629,7 +633,10 @@ composite_bwd_kernel(const CompositeParams p) {
     }
     // flush of the previous batch (complete: every warp passed the barrier above after it)
     if (cb > 0) flush_batch<CC, B>(p, s_acc + (buf ^ 1) * ACC, s_ids + ((cb - 1) & 3) * B, B);
-    if (stop) break;
+    if (stop) {  // batches 0..cb were staged (all of them when cb == n_batches)
+      if (p.stats && threadIdx.x == 0) atomicAdd(p.stats + 1, (unsigned long long)min(n_this, (cb + 1) * B));
+      break;
+    }
     const int nb = min(B, n_this - cb * B);
     {
       uint32_t rec_a = smem_u32(s_rec + buf * B * 3);
@@ -804,11 +811,18 @@ static int launch_bwd(const CompositeParams &p, uint32_t n_tiles, cudaStream_t s
 
 static bool aligned16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 
+static unsigned long long *g_stage_counters = nullptr;  // gs3d_set_stage_counters
+
 }  // namespace gs3d
 
 using namespace gs3d;
 
 extern "C" {
+
+int gs3d_set_stage_counters(uint64_t *counters) {
+  g_stage_counters = reinterpret_cast<unsigned long long *>(counters);
+  return GS3D_OK;
+}
 
 int gs3d_composite_sh_forward(uint32_t M, const float *records, const float *sh_coeffs,
                               uint32_t sh_stride_g, uint32_t sh_stride_c, const int32_t *start,
@@ -834,6 +848,7 @@ int gs3d_composite_sh_forward(uint32_t M, const float *records, const float *sh_
   p.ntw = n_tiles_w; p.nth = n_tiles_h; p.psx = pixel_size_x; p.psy = pixel_size_y;
   p.H = H; p.W = W; p.thresh = thresh; p.bg = bg_rgb; p.final_T = final_T; p.n_contrib = n_contrib;
   p.exact = exact_decisions;
+  p.stats = g_stage_counters;
   const uint32_t CC = C * C;
   p.sh_vec = (CC % 4 == 0) && (sh_stride_g % 4 == 0) && (sh_stride_c % 4 == 0) && aligned16(sh_coeffs);
   cudaStream_t st = as_stream(stream);
@@ -879,6 +894,7 @@ int gs3d_composite_sh_backward_peers(uint32_t M, const float *records, const flo
   p.g_mean = grad_mean2d; p.g_cov = grad_cov2d; p.g_sh = grad_sh; p.g_alpha = grad_alpha;
   p.gsh_sg = gsh_stride_g; p.gsh_sc = gsh_stride_c;
   p.touched = touched;
+  p.stats = g_stage_counters;
   const uint32_t CC = C * C;
   p.sh_vec = (CC % 4 == 0) && (sh_stride_g % 4 == 0) && (sh_stride_c % 4 == 0) && aligned16(sh_coeffs);
   p.gsh_vec = (CC % 4 == 0) && (gsh_stride_g % 4 == 0) && (gsh_stride_c % 4 == 0) && aligned16(grad_sh);

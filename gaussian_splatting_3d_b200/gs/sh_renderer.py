@@ -24,7 +24,8 @@ import torch
 from ..utils.activations import activations, inv_activations
 from ..utils.misc import print_info
 from ..utils.schedulers import lr_schedulers
-from ..utils.transforms import qvec2rotmat_batched
+from .. import ops
+from ..optim import FusedAdam
 from .backend import _backend  # noqa: F401  (import fails loudly when the CUDA library is missing)
 from .renderer import splat_sh, step_check
 
@@ -283,61 +284,57 @@ class SHRenderer(torch.nn.Module):
     def split_gaussians_by_radius(self):
         pass
 
+    def _hot_classes(self):
+        """KEEP / CLONE / SPLIT class per Gaussian (sh_renderer.py:433-456), one kernel."""
+        if self.split_type not in ("mean_grad", "2d_mean_grad"):
+            raise NotImplementedError
+        if self.split_reduction not in ("mean", "max"):
+            raise NotImplementedError
+        return ops.adc_classify(self.grad_mean, self.cnt, self.split_reduction, self.pos_grad_thresh,
+                                self.svec_before_activation.data, self._svec_code, self.split_scale_thresh)
+
     def split_gaussians(self):
         """Clone small / split large Gaussians whose accumulated positional gradient exceeds
         pos_grad_thresh (sh_renderer.py:426-540).  Output order: untouched + to-be-cloned originals,
-        then the clones, then two samples per split Gaussian with scales / scale_shrink_factor."""
+        then the clones, then two samples per split Gaussian with scales / scale_shrink_factor.
+        The reference's ~60 mask gathers / cats run as classify -> block scan -> one row mover; the
+        `torch.randn(num_split * 2, 3)` draw stays a torch call so the RNG stream is unchanged."""
         assert self.mean.grad is not None, (
             "mean.grad is None while clone or split gaussians are performed according to spatial "
             "gradient of mean")
-        if self.split_type not in ("mean_grad", "2d_mean_grad"):
-            raise NotImplementedError
-        if self.split_reduction == "mean":
-            hot = self.grad_mean / (self.cnt + 1e-5) > self.pos_grad_thresh
-        elif self.split_reduction == "max":
-            hot = self.grad_mean > self.pos_grad_thresh
-        else:
-            raise NotImplementedError
-        big = (self.svec.data > self.split_scale_thresh).any(dim=-1)
-        split_mask = hot & big
-        clone_mask = hot & ~split_mask
-        num_split = int(split_mask.sum().item())
-        num_clone = int(clone_mask.sum().item())
+        plan, (n_stay, num_clone, num_split) = ops.adc_plan(self._hot_classes())
         print(f"Splitting Gaussians: num_split {num_split} num_clone {num_clone}")
+        noise = torch.randn(num_split * 2, 3, device=self.mean.device)
         old = self._param_data()
-        keep = ~split_mask
-        twice = lambda t: t[split_mask].repeat(2, *([1] * (t.dim() - 1)))  # noqa: E731
-        s_mean, s_qvec = twice(old["mean"]), twice(old["qvec"])
-        s_svec = twice(self.svec.data)
-        rot_t = qvec2rotmat_batched(s_qvec).transpose(-1, -2)
-        noise = torch.randn(num_split * 2, 3, device=self.mean.device) * s_svec
-        s_mean = s_mean + torch.einsum("bij, bj -> bi", rot_t, noise)
-        new = {
-            "mean": torch.cat([old["mean"][keep], old["mean"][clone_mask], s_mean]),
-            "qvec": torch.cat([old["qvec"][keep], old["qvec"][clone_mask], s_qvec]),
-            "svec_before_activation": torch.cat([
-                old["svec_before_activation"][keep], old["svec_before_activation"][clone_mask],
-                self.svec_inv_act(s_svec / self.scale_shrink_factor)]),
-            "sh_coeffs": torch.cat([old["sh_coeffs"][keep], old["sh_coeffs"][clone_mask],
-                                    twice(old["sh_coeffs"])]),
-            "alpha_before_activation": torch.cat([
-                old["alpha_before_activation"][keep], old["alpha_before_activation"][clone_mask],
-                twice(old["alpha_before_activation"])]),
-        }
+        new = ops.adc_apply(plan, old["mean"], old["qvec"], old["svec_before_activation"], old["sh_coeffs"],
+                            old["alpha_before_activation"], self._svec_code, self.scale_shrink_factor, noise)
         expected = self.N + num_split + num_clone
-        self._set_params(new)
+        self._set_params(dict(zip(_PARAM_NAMES, (new[0], new[1], new[2], new[3], new[4]))))
         assert self.N == expected
         print(f"num gaussians: {self.N}")
         del old, new
         gc.collect()
 
     def select_masked_gaussians(self, mask):
-        self._set_params({k: v[mask] for k, v in self._param_data().items()})
+        """Keep the Gaussians with mask True (sh_renderer.py:731-741): scan + one fused row mover
+        instead of five boolean-mask gathers."""
+        mask = mask.contiguous()
+        if mask.dtype != torch.bool:
+            mask = mask != 0
+        plan, _ = ops.adc_plan(mask)
+        old = self._param_data()
+        new = ops.adc_apply(plan, old["mean"], old["qvec"], old["svec_before_activation"], old["sh_coeffs"],
+                            old["alpha_before_activation"], self._svec_code)
+        self._set_params(dict(zip(_PARAM_NAMES, (new[0], new[1], new[2], new[3], new[4]))))
 
     def remove_low_alpha_gaussians(self):
         before = self.N
-        self.select_masked_gaussians(
-            self.alpha_act(self.alpha_before_activation.data) >= self.alpha_thresh)
+        cls = ops.adc_classify_alpha(self.alpha_before_activation.data, self._alpha_code, self.alpha_thresh)
+        plan, _ = ops.adc_plan(cls)
+        old = self._param_data()
+        new = ops.adc_apply(plan, old["mean"], old["qvec"], old["svec_before_activation"], old["sh_coeffs"],
+                            old["alpha_before_activation"], self._svec_code)
+        self._set_params(dict(zip(_PARAM_NAMES, (new[0], new[1], new[2], new[3], new[4]))))
         print(f"remove_low_alpha_gaussians: removed {before - self.N}, remaining {self.N}")
 
     @torch.no_grad()
@@ -429,7 +426,12 @@ class SHRenderer(torch.nn.Module):
     def get_optimizer(self, epoch):
         groups = [{"params": p, "lr": self.scheduler[name](epoch)}
                   for name, p in self.get_param_groups().items()]
-        return torch.optim.Adam(groups, lr=self.cfg.lr, betas=(0.9, 0.99))
+        if not self.cfg.get("fused_adam", True):
+            return torch.optim.Adam(groups, lr=self.cfg.lr, betas=(0.9, 0.99))
+        # same interface and arithmetic, one launch for all five groups; `adam_single_step: true` is for
+        # loops that, like main_sh.py:238, re-create the optimiser after every step (no moment buffers)
+        return FusedAdam(groups, lr=self.cfg.lr, betas=(0.9, 0.99),
+                         single_step=self.cfg.get("adam_single_step", False))
 
     def vis_grads_gaussians(self, thresh):
         self.select_masked_gaussians(self.mean_2d.grad.norm(dim=-1) > thresh)

@@ -381,3 +381,109 @@ def clip_rects_to_rows(aabb_topleft, aabb_bottomright, depth, row_begin, row_end
                                            _stream(depth)), "clip_rects_to_rows")
     m = int(counts[0])
     return tl[:m], br[:m], dp[:m], idx[:m], int(counts[1])
+
+
+# ---------------------------------------------------------------- measurement aid
+def set_stage_counters(counters):
+    """counters: int64 [2] CUDA tensor (zeroed) or None; see gs3d_set_stage_counters."""
+    if counters is not None:
+        _chk(counters, "counters", _I64)
+        if counters.numel() < 2:
+            raise RuntimeError("counters must hold two int64 values")
+    check(capi.lib.gs3d_set_stage_counters(ptr(counters)), "set_stage_counters")
+
+
+# ---------------------------------------------------------------- optimiser step (8f rank 1)
+def adam_step(params, grads, exp_avgs, exp_avg_sqs, lrs, beta1, beta2, eps, step, state_mode=0):
+    """One Adam step over up to 8 tensors in one launch (see gs3d_adam_step).  exp_avgs / exp_avg_sqs
+    may be None with state_mode 2."""
+    n = len(params)
+    if not (len(grads) == n and len(lrs) == n):
+        raise RuntimeError("adam_step: params / grads / lrs differ in length")
+    if n == 0:
+        return
+    segs = (capi.AdamSegment * n)()
+    for i in range(n):
+        p, g = _chk(params[i], "param", _F32), _chk(grads[i], "grad", _F32)
+        if g.numel() != p.numel() or g.device != p.device:
+            raise RuntimeError("adam_step: grad does not match its parameter")
+        m = v = None
+        if state_mode != 2:
+            m, v = _chk(exp_avgs[i], "exp_avg", _F32), _chk(exp_avg_sqs[i], "exp_avg_sq", _F32)
+            if m.numel() != p.numel() or v.numel() != p.numel():
+                raise RuntimeError("adam_step: moment buffer does not match its parameter")
+        segs[i] = capi.AdamSegment(p.data_ptr(), g.data_ptr(), m.data_ptr() if m is not None else None,
+                                   v.data_ptr() if v is not None else None, p.numel(), float(lrs[i]))
+    check(capi.lib.gs3d_adam_step(n, segs, float(beta1), float(beta2), float(eps), int(step), int(state_mode),
+                                  _stream(params[0])), "adam_step")
+
+
+# ---------------------------------------------------------------- adaptive density control (8f rank 1)
+ADC_KEEP, ADC_CLONE, ADC_SPLIT, ADC_DROP = 0, 1, 2, 3
+
+
+def adc_classify(grad_mean_acc, cnt, reduction, pos_grad_thresh, svec_param, svec_act, split_scale_thresh):
+    """-> cls uint8 [N] (KEEP / CLONE / SPLIT), sh_renderer.py:433-456.  reduction: "max" | "mean"."""
+    _chk(grad_mean_acc, "grad_mean", _F32)
+    _chk(svec_param, "svec_before_activation", _F32)
+    red = {"max": 1, "mean": 2}.get(reduction)
+    if red is None:
+        raise NotImplementedError(reduction)
+    if red == 2:
+        _chk(cnt, "cnt", _I32)
+    N = grad_mean_acc.numel()
+    cls = torch.empty(N, dtype=_U8, device=grad_mean_acc.device)
+    check(capi.lib.gs3d_adc_classify(N, ptr(grad_mean_acc), ptr(cnt) if red == 2 else None, red,
+                                     float(pos_grad_thresh), ptr(svec_param), int(svec_act),
+                                     float(split_scale_thresh), ptr(cls), _stream(cls)), "adc_classify")
+    return cls
+
+
+def adc_classify_alpha(alpha_param, alpha_act, alpha_thresh):
+    """-> cls uint8 [N]: KEEP iff act(alpha) >= thresh else DROP (sh_renderer.py:542-543)."""
+    _chk(alpha_param, "alpha_before_activation", _F32)
+    N = alpha_param.numel()
+    cls = torch.empty(N, dtype=_U8, device=alpha_param.device)
+    check(capi.lib.gs3d_adc_classify_alpha(N, ptr(alpha_param), int(alpha_act), float(alpha_thresh), ptr(cls),
+                                           _stream(cls)), "adc_classify_alpha")
+    return cls
+
+
+def adc_plan(cls):
+    """cls: uint8 classes or a torch.bool keep mask.  -> (plan, (n_stay, n_clone, n_split)); syncs."""
+    _chk(cls, "cls", (_U8, _BOOL))
+    N = cls.numel()
+    scratch = _scratch(capi.lib.gs3d_adc_scratch_bytes(N), cls.device)
+    counts = (C.c_int64 * 3)(0, 0, 0)
+    check(capi.lib.gs3d_adc_plan(N, ptr(cls), 1 if cls.dtype == _BOOL else 0, C.cast(counts, _I64P_t),
+                                 ptr(scratch), scratch.numel(), _stream(cls)), "adc_plan")
+    return (cls, scratch, counts), (int(counts[0]), int(counts[1]), int(counts[2]))
+
+
+def adc_apply(plan, mean, qvec, svec_param, sh_coeffs, alpha_param, svec_act=1, scale_shrink_factor=1.0,
+              noise=None):
+    """-> the five new parameter tensors (see gs3d_adc_apply)."""
+    cls, scratch, counts = plan
+    for t, n in ((mean, "mean"), (qvec, "qvec"), (svec_param, "svec_before_activation"),
+                 (sh_coeffs, "sh_coeffs"), (alpha_param, "alpha_before_activation")):
+        _chk(t, n, _F32)
+    N = mean.size(0)
+    if cls.numel() != N:
+        raise RuntimeError("adc_apply: plan was made for a different N")
+    n_out = int(counts[0]) + int(counts[1]) + 2 * int(counts[2])
+    if int(counts[2]):
+        _chk(noise, "noise", _F32)
+        if noise.numel() != 6 * int(counts[2]):
+            raise RuntimeError("adc_apply: noise must be [2*n_split, 3]")
+    dev = mean.device
+    sh_width = sh_coeffs[0].numel() if N else 0
+    out = (torch.empty(n_out, 3, dtype=_F32, device=dev), torch.empty(n_out, 4, dtype=_F32, device=dev),
+           torch.empty(n_out, 3, dtype=_F32, device=dev),
+           torch.empty((n_out,) + tuple(sh_coeffs.shape[1:]), dtype=_F32, device=dev),
+           torch.empty(n_out, dtype=_F32, device=dev))
+    check(capi.lib.gs3d_adc_apply(N, ptr(cls), 1 if cls.dtype == _BOOL else 0, ptr(scratch),
+                                  C.cast(counts, _I64P_t), ptr(mean), ptr(qvec), ptr(svec_param), ptr(sh_coeffs),
+                                  ptr(alpha_param), int(sh_width), int(svec_act), float(scale_shrink_factor),
+                                  ptr(noise) if noise is not None else None, ptr(out[0]), ptr(out[1]), ptr(out[2]),
+                                  ptr(out[3]), ptr(out[4]), _stream(mean)), "adc_apply")
+    return out

@@ -262,6 +262,70 @@ int gs3d_clip_rects_to_rows(uint32_t N, const int32_t *aabb_topleft, const int32
                             int32_t *br_out, float *depth_out, int32_t *index_out, int64_t *counts_host,
                             void *scratch, size_t scratch_bytes, void *stream);
 
+/* ---- measurement aid: when set (device pointer to two zero-initialised uint64 counters, NULL to
+ * disable), every compositing launch adds the number of duplicates it actually STAGED into shared
+ * memory to counters[0] (forward) / counters[1] (backward) -- one atomic per tile.  Tiles stop staging
+ * once all their pixels are saturated, so this is the unit count behind bench.py's roofline. */
+int gs3d_set_stage_counters(uint64_t *counters);
+
+/* ======== the steps either side of the rasteriser in the training loop ======== */
+
+/* ---- `opt.step()` (main_sh.py:193) of the torch.optim.Adam built by SHRenderer.get_optimizer
+ * (sh_renderer.py:720-729: one group per parameter tensor with its own lr, betas (0.9, 0.99), eps 1e-8,
+ * no weight decay, no amsgrad), all groups in ONE launch.  Arithmetic follows torch's
+ * `_single_tensor_adam` (lerp, mul/addcmul, sqrt/div/add, addcdiv); bias corrections are formed on the
+ * host in double like torch's Python scalars.  `step` counts from 1 and is the value AFTER the increment.
+ * state_mode 0: general step (moments read and written, 28 B/element);
+ * state_mode 1: step == 1, moments are taken as zero and written but not read (20 B/element);
+ * state_mode 2: step == 1, moments neither read nor written, exp_avg/exp_avg_sq may be NULL
+ *               (12 B/element) -- the reference re-creates the optimiser after every step
+ *               (main_sh.py:238), so every step it ever takes is such a first step. */
+typedef struct gs3d_adam_segment {
+  float *param;
+  const float *grad;
+  float *exp_avg;
+  float *exp_avg_sq;
+  uint64_t n; /* elements */
+  double lr;
+} gs3d_adam_segment;
+int gs3d_adam_step(int n_segments, const gs3d_adam_segment *segments_host, double beta1, double beta2,
+                   double eps, uint32_t step, int state_mode, void *stream);
+
+/* ---- adaptive density control: split_gaussians / remove_low_alpha_gaussians / select_masked_gaussians
+ * (sh_renderer.py:426-600, 731-741) as classify -> plan (deterministic block scan) -> apply (one fused row
+ * mover).  Classes: */
+#define GS3D_ADC_KEEP 0  /* row stays */
+#define GS3D_ADC_CLONE 1 /* row stays and is copied once after the kept rows */
+#define GS3D_ADC_SPLIT 2 /* row is replaced by two samples after the clones */
+#define GS3D_ADC_DROP 3  /* row is removed */
+/* sh_renderer.py:433-456: hot = grad_mean_acc > pos_grad_thresh (reduction 1, "max") or
+ * grad_mean_acc / (cnt + 1e-5) > pos_grad_thresh (reduction 2, "mean"); a hot Gaussian is SPLIT when any
+ * activated scale exceeds split_scale_thresh, else CLONE; everything else KEEP.  cls u8 [N]. */
+int gs3d_adc_classify(uint32_t N, const float *grad_mean_acc, const int32_t *cnt, int reduction,
+                      float pos_grad_thresh, const float *svec_param, int svec_act, float split_scale_thresh,
+                      uint8_t *cls, void *stream);
+/* sh_renderer.py:542-560: KEEP iff act(alpha_param) >= alpha_thresh, else DROP. */
+int gs3d_adc_classify_alpha(uint32_t N, const float *alpha_param, int alpha_act, float alpha_thresh,
+                            uint8_t *cls, void *stream);
+/* Counts and per-block offsets.  cls_is_keep_mask != 0: cls is a torch.bool keep mask (non-zero = KEEP,
+ * zero = DROP; select_masked_gaussians).  counts_host[0] = rows that stay (KEEP + CLONE), [1] = CLONE,
+ * [2] = SPLIT, valid on return (one 24-byte D2H + stream sync: the reference's `.sum().item()`,
+ * sh_renderer.py:458-459).  The new N is counts[0] + counts[1] + 2*counts[2].  The offsets are left in
+ * `scratch` (>= gs3d_adc_scratch_bytes(N) bytes) for gs3d_adc_apply. */
+size_t gs3d_adc_scratch_bytes(uint32_t N);
+int gs3d_adc_plan(uint32_t N, const uint8_t *cls, int cls_is_keep_mask, int64_t *counts_host, void *scratch,
+                  size_t scratch_bytes, void *stream);
+/* Writes the new parameter tensors in the reference's order (sh_renderer.py:485-527):
+ * [KEEP and CLONE rows in index order | CLONE rows again | first split samples | second split samples].
+ * Split samples: mean + R(q)^T (noise * svec), scales svec / scale_shrink_factor through the inverse
+ * activation, other fields copied; noise [2*counts[2], 3] standard normal (torch.randn in the caller so
+ * that the RNG stream is the reference's).  sh_width = 3 * max_C^2 floats per row. */
+int gs3d_adc_apply(uint32_t N, const uint8_t *cls, int cls_is_keep_mask, const void *plan_scratch,
+                   const int64_t *counts_host, const float *mean, const float *qvec, const float *svec_param,
+                   const float *sh_coeffs, const float *alpha_param, uint32_t sh_width, int svec_act,
+                   float scale_shrink_factor, const float *noise, float *mean_out, float *qvec_out,
+                   float *svec_param_out, float *sh_coeffs_out, float *alpha_param_out, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

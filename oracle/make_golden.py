@@ -14,6 +14,9 @@ Fixtures:
                        seeded upstream gradient) and gs.culling.tile_culling_aabb_count
   frustum_<name>.npz   CameraInfo.get_frustum
   kat.json             known-answer values (test/gaussian_test.py run here; SURVEY.md 8c values)
+  adc_<reduction>.npz  inputs + outputs of the REAL SHRenderer.split_gaussians /
+                       remove_low_alpha_gaussians (gs/sh_renderer.py:426-560) on CPU, with the
+                       torch.randn draw of :470 recorded (`--adc-only` regenerates just these)
 """
 import json
 import sys
@@ -98,6 +101,9 @@ def main():
 
     GOLD.mkdir(parents=True, exist_ok=True)
     torch.set_num_threads(1)
+    make_adc_golden()
+    if "--adc-only" in sys.argv:
+        return
     cases = [("cfg1", 0, 2000), ("cfg2", 3, 3000), ("cfg3", 5, 1500)]
     # a rotated / translated camera as well, so W != I is exercised
     for name, seed, n in cases:
@@ -146,6 +152,58 @@ def main():
     }
     (GOLD / "kat.json").write_text(json.dumps(kat, indent=1))
     print("kat", kat["gaussian_test"])
+
+
+def make_adc_golden():
+    """Run the reference's own split_gaussians / remove_low_alpha_gaussians on a small seeded model."""
+    from gs.sh_renderer import SHRenderer  # noqa: E402  (REAL reference)
+    from utils.activations import activations, inv_activations  # noqa: E402
+
+    for reduction in ("mean", "max"):
+        g = torch.Generator().manual_seed(11 if reduction == "mean" else 12)
+        N, maxC = 600, 4
+        p = {
+            "mean": torch.randn(N, 3, generator=g) * 2.0,
+            "qvec": torch.randn(N, 4, generator=g),
+            "svec_before_activation": torch.log(torch.exp(torch.rand(N, 3, generator=g) * 3.0 - 6.5)),
+            "sh_coeffs": torch.randn(N, 3, maxC * maxC, generator=g),
+            "alpha_before_activation": torch.randn(N, generator=g) * 3.0,
+        }
+        cnt = torch.randint(0, 6, (N,), generator=g, dtype=torch.int32)
+        grad_mean = torch.rand(N, generator=g) * (4e-4 if reduction == "max" else 1.2e-3)
+        r = SHRenderer.__new__(SHRenderer)
+        torch.nn.Module.__init__(r)
+        r.device = "cpu"
+        r.N, r.max_C = N, maxC
+        for k, v in p.items():
+            setattr(r, k, torch.nn.Parameter(v.clone()))
+        r.mean.grad = torch.zeros_like(r.mean)
+        r.grad_mean, r.cnt = grad_mean.clone(), cnt.clone()
+        r.svec_act, r.alpha_act = activations["exp"], activations["sigmoid"]
+        r.svec_inv_act, r.alpha_inv_act = inv_activations["exp"], inv_activations["sigmoid"]
+        r.split_type, r.split_reduction = "2d_mean_grad", reduction
+        r.pos_grad_thresh, r.split_scale_thresh, r.scale_shrink_factor = 2e-4, 0.01, 1.6
+        r.alpha_thresh = 0.05
+        torch.manual_seed(77)
+        r.split_gaussians()
+        out = {k: getattr(r, k).data.clone() for k in p}
+        n_after_split = r.N
+        num_new = n_after_split - N
+        # the draw of sh_renderer.py:470 is the first use of the global CPU generator after the seed
+        hot = (grad_mean / (cnt + 1e-5) if reduction == "mean" else grad_mean) > 2e-4
+        num_split = int((hot & (torch.exp(p["svec_before_activation"]) > 0.01).any(dim=-1)).sum())
+        torch.manual_seed(77)
+        noise = torch.randn(num_split * 2, 3)
+        r.remove_low_alpha_gaussians()
+        pruned = {k: getattr(r, k).data.clone() for k in p}
+        np.savez_compressed(
+            GOLD / f"adc_{reduction}.npz",
+            **{f"in_{k}": v.numpy() for k, v in p.items()}, cnt=cnt.numpy(), grad_mean=grad_mean.numpy(),
+            noise=noise.numpy(), num_split=np.int64(num_split), num_new=np.int64(num_new),
+            settings=np.array([2e-4, 0.01, 1.6, 0.05]),
+            **{f"split_{k}": v.numpy() for k, v in out.items()},
+            **{f"pruned_{k}": v.numpy() for k, v in pruned.items()})
+        print("adc", reduction, "N", N, "->", n_after_split, "->", r.N, "num_split", num_split)
 
 
 def _posed_c2w():

@@ -15,6 +15,8 @@ reference functions (imported from /root/reference by oracle/make_golden.py) tha
   camera_space_to_pixel_space   utils/camera.py:290-303
   tile_culling_aabb_count   gs/culling.py:8-37
   reference_forward         gs/sh_renderer.py:188-316 (+ activations :318-324)
+  split_gaussians / select_masked_gaussians / remove_low_alpha_mask   gs/sh_renderer.py:426-560,731-741
+  adam_first_step           torch.optim.Adam as main_sh.py:193,238 uses it (re-created every step)
 """
 import numpy as np
 import torch
@@ -193,3 +195,84 @@ def reference_forward(params, c2w, cam, C, tile_size=16, frustum_radius=1.0, til
         return img, dict(mask=mask, mean2d=mean2d, cov=cov, depth=depth, tl=tl, br=br, n_dub=n_dub,
                          ids=ids, start=start, end=end, keys=keys, alpha=alpha, sh=sh, JW=JW)
     return img
+
+
+# ---------------------------------------------------------------- adaptive density control (8f rank 1)
+
+def split_masks(grad_mean, cnt, svec, split_reduction, pos_grad_thresh, split_scale_thresh):
+    """sh_renderer.py:433-456 -> (split_mask, clone_mask)."""
+    if split_reduction == "mean":
+        mask = grad_mean / (cnt + 1e-5) > pos_grad_thresh
+    elif split_reduction == "max":
+        mask = grad_mean > pos_grad_thresh
+    else:
+        raise NotImplementedError
+    svec_mask = (svec > split_scale_thresh).any(dim=-1)
+    split_mask = torch.logical_and(mask, svec_mask)
+    clone_mask = torch.logical_and(mask, torch.logical_not(split_mask))
+    return split_mask, clone_mask
+
+
+def split_gaussians(params, grad_mean, cnt, split_reduction, pos_grad_thresh, split_scale_thresh,
+                    scale_shrink_factor, noise=None, svec_act=torch.exp, svec_inv_act=torch.log):
+    """sh_renderer.py:426-540 op for op.  params: dict of the five tensors (mean, qvec,
+    svec_before_activation, sh_coeffs, alpha_before_activation).  `noise` replaces the
+    `torch.randn(num_split * 2, 3)` draw of :470 (None: draw it here, like the reference).
+    -> (new params dict, num_split, num_clone)."""
+    mean, qvec = params["mean"], params["qvec"]
+    svec_ba, sh, alpha_ba = params["svec_before_activation"], params["sh_coeffs"], params["alpha_before_activation"]
+    svec = svec_act(svec_ba)
+    split_mask, clone_mask = split_masks(grad_mean, cnt, svec, split_reduction, pos_grad_thresh, split_scale_thresh)
+    num_split = int(split_mask.sum().item())
+    num_clone = int(clone_mask.sum().item())
+    split_mean = mean[split_mask].repeat(2, 1)
+    split_qvec = qvec[split_mask].repeat(2, 1)
+    split_svec = svec[split_mask].repeat(2, 1)
+    split_sh = sh[split_mask].repeat(2, 1, 1)
+    split_alpha = alpha_ba[split_mask].repeat(2)
+    split_rotmat = quaternion_to_rotation_matrix(split_qvec).transpose(-1, -2)
+    if noise is None:
+        noise = torch.randn(num_split * 2, 3, device=mean.device)
+    split_gn = noise * split_svec
+    split_sampled_mean = split_mean + torch.einsum("bij, bj -> bi", split_rotmat, split_gn)
+    N_old = mean.shape[0]
+    unchanged = N_old - num_split
+    N = N_old + num_split + num_clone
+    new = {
+        "mean": torch.zeros([N, 3]), "qvec": torch.zeros([N, 4]), "svec_before_activation": torch.zeros([N, 3]),
+        "sh_coeffs": torch.zeros([N] + list(sh.shape[1:])), "alpha_before_activation": torch.zeros([N]),
+    }
+    keep = ~split_mask
+    for k in new:
+        new[k][:unchanged] = params[k][keep]
+        new[k][unchanged:unchanged + num_clone] = params[k][clone_mask]
+    pts = unchanged + num_clone
+    new["mean"][pts:pts + 2 * num_split] = split_sampled_mean
+    new["qvec"][pts:pts + 2 * num_split] = split_qvec
+    new["sh_coeffs"][pts:pts + 2 * num_split] = split_sh
+    new["alpha_before_activation"][pts:pts + 2 * num_split] = split_alpha
+    new["svec_before_activation"][pts:pts + 2 * num_split] = svec_inv_act(split_svec / scale_shrink_factor)
+    assert pts + 2 * num_split == N
+    return new, num_split, num_clone
+
+
+def select_masked_gaussians(params, mask):
+    """sh_renderer.py:731-741 (also :542-560, :590-600): boolean-mask gather of the five tensors."""
+    return {k: v[mask] for k, v in params.items()}
+
+
+def remove_low_alpha_mask(alpha_ba, alpha_thresh, alpha_act=torch.sigmoid):
+    """sh_renderer.py:543."""
+    return alpha_act(alpha_ba) >= alpha_thresh
+
+
+def adam_first_step(params, grads, lrs, betas=(0.9, 0.99), eps=1e-8):
+    """One step of a freshly created torch.optim.Adam (the only kind main_sh.py ever takes: the optimiser
+    is re-created after every step, main_sh.py:238), with sh_renderer.py:720-729's per-tensor lrs.
+    Uses torch.optim.Adam itself; params are updated in place."""
+    ps = [torch.nn.Parameter(p) for p in params]
+    for p, g in zip(ps, grads):
+        p.grad = g
+    opt = torch.optim.Adam([{"params": [p], "lr": lr} for p, lr in zip(ps, lrs)], lr=1e-3, betas=betas, eps=eps)
+    opt.step()
+    return [p.data for p in ps], opt

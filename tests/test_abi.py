@@ -39,11 +39,13 @@ def test_ctypes_signatures_match_header():
         assert len(sig) == len(a), name
         for decl, t in zip(a, sig):
             if "*" in decl:
-                assert t in (C.c_void_p, capi._CAM, capi._I64P), (name, decl)
+                assert t in (C.c_void_p, capi._CAM, capi._I64P, capi._ADAM), (name, decl)
             elif decl.startswith("uint32_t"):
                 assert t is C.c_uint32, (name, decl)
             elif decl.startswith("float"):
                 assert t is C.c_float, (name, decl)
+            elif decl.startswith("double"):
+                assert t is C.c_double, (name, decl)
             elif decl.startswith("size_t"):
                 assert t is C.c_size_t, (name, decl)
             else:

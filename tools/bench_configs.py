@@ -60,24 +60,37 @@ def main():
     c2w = sc["c2w"].to(dev)
     out = {"config": which, "N": r.N, "C": C, "image": [cam.w, cam.h], "n_gpus": world, "steps": steps}
     if which == "cfg3":
-        r.train()
-        r.fuse_adc = True
+        # the reference's loop body (main_sh.py:150-238): forward, loss, zero_grad, backward, step,
+        # adaptive_control (statistics only between the structural iterations), optimiser RE-CREATED
         tgt = S.make_target(cam, 0).to(dev)
-        opt = r.get_optimizer(0)
+        variants = {}
+        for vname, over in (("fused_single_step", dict(fused_adam=True, adam_single_step=True)),
+                            ("fused", dict(fused_adam=True, adam_single_step=False)),
+                            ("torch_adam", dict(fused_adam=False))):
+            r = S.renderer_from_scene(sc, S.make_cfg(device=str(dev), sh_order=C, warm_up=0, **over))
+            r.train()
+            r.fuse_adc = True
+            state = {"opt": r.get_optimizer(0), "e": 0}
 
-        def step():
-            o = r(c2w, cam)
-            loss = ((o - tgt) ** 2).mean()
-            opt.zero_grad(set_to_none=True)
-            loss.backward()
-            r.update_grads()
-            opt.step()
+            def step(r=r, state=state):
+                o = r(c2w, cam)
+                loss = ((o - tgt) ** 2).mean()
+                state["opt"].zero_grad()
+                loss.backward()
+                state["opt"].step()
+                r.adaptive_control(state["e"])
+                state["opt"] = r.get_optimizer(state["e"])
+                state["e"] += 1
 
-        for _ in range(3):
-            step()
-        ms = timed(step, steps, world, dev)
-        out.update({"metric": "full training steps/s (fwd + L2 + bwd + ADC accumulation + Adam)",
-                    "ms_per_step": ms, "value": 1000.0 / ms, "n_dub": r.total_dub_gaussians})
+            for _ in range(3):
+                step()
+            variants[vname] = timed(step, steps, world, dev)
+            del r, state
+            torch.cuda.empty_cache()
+        ms = variants["fused_single_step"]
+        out.update({"metric": "full training steps/s (fwd + L2 + bwd + ADC accumulation + Adam, optimiser "
+                              "re-created every step like main_sh.py:238)",
+                    "ms_per_step": ms, "value": 1000.0 / ms, "ms_per_step_by_optimiser": variants})
     elif which == "cfg4":
         mode = sys.argv[3] if len(sys.argv) > 3 else "push"
         r.train()
