@@ -218,10 +218,11 @@ def run_ours(args, rank, local_rank, world):
             tgt = tgt_host.to(dev, non_blocking=True)
         else:
             c2w, tgt = c2w_dev, tgt_dev
+        if world > 1:
+            flat.zero()  # per-step reset of the gradient buffers (side stream: overlaps the forward)
         out = r(c2w, cam)
         loss = ((out - tgt) ** 2).mean()
         if world > 1:
-            flat.zero()
             flat.backward_into(loss)
             flat.exchange()
         else:

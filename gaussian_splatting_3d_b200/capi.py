@@ -72,7 +72,7 @@ SIGNATURES = {
     "gs3d_rows_scatter": (_i, [_i, _P, _P, _P, _u32, _P, _u32, _P]),
     "gs3d_rows_push_marked": (_i, [_P, _u32, _i, _P, _P, _P, _P, _P, _i, _P, _P]),
     "gs3d_rows_zero_marked": (_i, [_P, _u32, _i, _P, _P, _i, _P]),
-    "gs3d_marks_broadcast": (_i, [_P, _u32, _P, _i, _P]),
+    "gs3d_marks_broadcast": (_i, [_P, _u32, _P, _i, _P, _P]),
     "gs3d_row_duplicate_counts": (_i, [_u32, _P, _P, _u32, _P, _P, _sz, _P]),
     "gs3d_clip_scratch_bytes": (_sz, [_u32]),
     "gs3d_clip_rects_to_rows": (_i, [_u32, _P, _P, _P, _i, _i, _P, _P, _P, _P, _I64P, _P, _sz, _P]),

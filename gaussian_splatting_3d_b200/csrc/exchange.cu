@@ -250,7 +250,29 @@ struct MarkArgs {
   uint32_t N;
   int n_peers;
   uint8_t *union_peer[8];
+  uint8_t *union_mc;  // NVSwitch multicast address of the union marks (or null)
 };
+
+// Multicast form: one thread per 16 marks; every non-zero 4-mark word is OR-ed into ALL ranks' union
+// marks by the switch with a single multimem.red.or.b32 -- 1/8 of the packets of the per-peer byte
+// stores at 8 ranks, and 4 marks per packet.
+__global__ void __launch_bounds__(256)
+marks_broadcast_mc_kernel(const MarkArgs a) {
+  const size_t c0 = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) * 16;
+  if (c0 + 16 > a.N) {  // tail (< 16 marks): per-peer byte stores
+    for (size_t g = c0; g < a.N; ++g)
+      if (a.marks[g])
+        for (int r = 0; r < a.n_peers; ++r) a.union_peer[r][g] = 1;
+    return;
+  }
+  const uint4 v = *reinterpret_cast<const uint4 *>(a.marks + c0);
+  const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+  for (int q = 0; q < 4; ++q)
+    if (w[q])
+      asm volatile("multimem.red.relaxed.sys.global.or.b32 [%0], %1;" ::"l"(a.union_mc + c0 + 4 * q), "r"(w[q])
+                   : "memory");
+}
 
 __global__ void __launch_bounds__(256)
 marks_broadcast_kernel(const MarkArgs a) {
@@ -320,7 +342,7 @@ int gs3d_rows_push_marked(const uint8_t *marks, uint32_t N, int n_blocks, const 
 }
 
 int gs3d_marks_broadcast(const uint8_t *marks, uint32_t N, const uint64_t *peer_union_ptrs_host, int n_peers,
-                         void *stream) {
+                         void *multicast_union, void *stream) {
   using namespace gs3d;
   GS3D_REQUIRE(n_peers >= 1 && n_peers <= 8, GS3D_EINVAL, "marks_broadcast: n_peers must be 1..8 (got %d)", n_peers);
   if (N == 0) return GS3D_OK;
@@ -331,7 +353,11 @@ int gs3d_marks_broadcast(const uint8_t *marks, uint32_t N, const uint64_t *peer_
     a.union_peer[r] = reinterpret_cast<uint8_t *>(static_cast<uintptr_t>(peer_union_ptrs_host[r]));
     GS3D_REQUIRE(a.union_peer[r], GS3D_EINVAL, "marks_broadcast: null peer pointer %d", r);
   }
-  marks_broadcast_kernel<<<div_up(N, 4096u), 256, 0, as_stream(stream)>>>(a);
+  a.union_mc = static_cast<uint8_t *>(multicast_union);
+  if (a.union_mc && (reinterpret_cast<uintptr_t>(marks) & 15) == 0 && (reinterpret_cast<uintptr_t>(a.union_mc) & 15) == 0)
+    marks_broadcast_mc_kernel<<<div_up(div_up(N, 16u), 256u), 256, 0, as_stream(stream)>>>(a);
+  else
+    marks_broadcast_kernel<<<div_up(N, 4096u), 256, 0, as_stream(stream)>>>(a);
   GS3D_LAUNCH_CHECK();
   return GS3D_OK;
 }

@@ -213,6 +213,8 @@ class _splat_sh(torch.autograd.Function):
                                   peer_ptrs=bufs.get("sh_peer_ptrs") if bufs else None,
                                   multicast_ptr=bufs.get("sh_multicast_ptr") if bufs else None,
                                   touched=bufs.get("touched") if bufs else None)
+        if bufs is not None and bufs.get("after_composite_backward") is not None:
+            bufs["after_composite_backward"]()  # e.g. the data-parallel mark broadcast, on a side stream
         gm, gq, gs, ga = ops.project_backward_fused(
             mask, mean, qvec, svec_p, alpha_p, svec_act, alpha_act, c2w, detach, g_mean2d, g_cov,
             g_alpha, grad_mean_acc=st.get("adc_acc"), adc_mode=st.get("adc_mode", 0), out=leaf_out,

@@ -322,13 +322,15 @@ def rows_zero_marked(marks, blocks, clear_marks=True):
                                          _stream(marks)), "rows_zero_marked")
 
 
-def marks_broadcast(marks, peer_union_ptrs):
-    """Set byte g of every rank's union marks for each g with marks[g] != 0."""
+def marks_broadcast(marks, peer_union_ptrs, multicast_union=None):
+    """Set byte g of every rank's union marks for each g with marks[g] != 0 (multicast_union: NVSwitch
+    multicast address of the union marks -> one multimem.red.or per non-zero 4-mark word)."""
     _chk(marks, "marks", _U8)
     n = len(peer_union_ptrs)
     uni = (C.c_uint64 * n)(*[int(x) for x in peer_union_ptrs])
-    check(capi.lib.gs3d_marks_broadcast(ptr(marks), marks.numel(), C.cast(uni, C.c_void_p), n, _stream(marks)),
-          "marks_broadcast")
+    check(capi.lib.gs3d_marks_broadcast(ptr(marks), marks.numel(), C.cast(uni, C.c_void_p), n,
+                                        C.c_void_p(int(multicast_union)) if multicast_union else None,
+                                        _stream(marks)), "marks_broadcast")
 
 
 def rows_pull_marked(union_marks, widths, offsets, peer_private_ptrs, peer_result_ptrs, rank,

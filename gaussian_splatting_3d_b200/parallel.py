@@ -99,9 +99,11 @@ class FlatGradients:
                     buf, h = (self.flat, self.handle) if b == 0 else symmetric(total, torch.float32)
                     uni, uh = symmetric(N, torch.uint8)
                     mc = int(h.multicast_ptr) if use_multicast else 0
+                    umc = int(uh.multicast_ptr) if use_multicast else 0
                     self._res.append(dict(flat=buf, handle=h, views=carve(buf)[0], union=uni,
                                           peer_ptrs=[int(p) for p in h.buffer_ptrs],
-                                          union_ptrs=[int(p) for p in uh.buffer_ptrs], multicast=mc if mc else None))
+                                          union_ptrs=[int(p) for p in uh.buffer_ptrs], multicast=mc if mc else None,
+                                          union_multicast=umc if umc else None))
                 self._cur = 0
                 self.union = self._res[0]["union"]
                 if self.pull:  # peers read this rank's private rows: symmetric (multicast-mapped) as well
@@ -127,9 +129,34 @@ class FlatGradients:
             self.multicast_ptr = mc if mc else None
         self.module = None
         self._dirty = False
+        # side stream for the per-step resets and the mark broadcast: they overlap the forward kernels and
+        # the projection backward instead of sitting on the critical path between two barriers
+        self._aux = torch.cuda.Stream(device=dev) if (self.push and dev.type == "cuda") else None
+        self._aux_ev = None
+
+    def _on_aux(self, fn):
+        """Run fn on the side stream after everything enqueued so far; returns the completion event."""
+        cur = torch.cuda.current_stream(self.flat.device)
+        self._aux.wait_stream(cur)
+        with torch.cuda.stream(self._aux):
+            fn()
+            ev = torch.cuda.Event()
+            ev.record(self._aux)
+        return ev
+
+    def _after_composite_backward(self):
+        """Called by the backward right after the compositing-backward launch (marks are final once it
+        completes): the mark broadcast runs beside the projection backward."""
+        from . import ops
+
+        cur = self._res[self._cur]
+        self._marks_ev = self._on_aux(lambda: ops.marks_broadcast(self.touched, cur["union_ptrs"],
+                                                                      cur["union_multicast"]))
 
     def attach(self, renderer):
         bufs = dict(zip(self.names, self.local_views if self.push else self.views))
+        if self.pull and self._aux is not None:
+            bufs["after_composite_backward"] = self._after_composite_backward
         if self.fused:
             bufs["sh_peer_ptrs"] = self.peer_ptrs
             bufs["sh_multicast_ptr"] = self.multicast_ptr
@@ -154,10 +181,20 @@ class FlatGradients:
         if self.push and self.module is not None:
             from . import ops
 
-            # this rank's private rows written last step (own marks); the result buffer of this step was
-            # already reset during the previous step's exchange()
-            ops.rows_zero_marked(self.touched, self.local_views, clear_marks=True)
-            cur = self._res[self._cur]
+            # (i) this rank's private rows written last step (own marks) and (ii) the OTHER result buffer --
+            # last step's sum, dead once zero() is called, pushed into again only after this step's final
+            # barrier -- are reset on the side stream while the forward kernels run
+            cur, nxt = self._res[self._cur], self._res[self._cur ^ 1]
+
+            def resets():
+                ops.rows_zero_marked(self.touched, self.local_views, clear_marks=True)
+                ops.rows_zero_marked(nxt["union"], nxt["views"], clear_marks=True)
+
+            if self._aux is not None:
+                self._aux_ev = self._on_aux(resets)
+            else:
+                resets()
+            self._marks_ev = None
             self.flat, self.views, self.union = cur["flat"], cur["views"], cur["union"]
         else:
             self.flat.zero_()
@@ -170,6 +207,9 @@ class FlatGradients:
 
     def backward_into(self, loss):
         """Run backward for `loss`; the kernels add the leaf gradients into the flat buffer."""
+        if self._aux_ev is not None:  # the private buffer must be clean before the backward adds into it
+            torch.cuda.current_stream(self.flat.device).wait_event(self._aux_ev)
+            self._aux_ev = None
         if self.module is None:
             loss.backward()  # plain autograd accumulation into the aliased .grad views
         else:
@@ -185,9 +225,17 @@ class FlatGradients:
         elif self.push and self.module is not None:
             from . import ops
 
-            cur, nxt = self._res[self._cur], self._res[self._cur ^ 1]
+            cur = self._res[self._cur]
+            stream = torch.cuda.current_stream(self.flat.device)
+            if self._aux_ev is not None:  # (no backward ran this step)
+                stream.wait_event(self._aux_ev)
+                self._aux_ev = None
             if self.pull:
-                ops.marks_broadcast(self.touched, cur["union_ptrs"])
+                if self._marks_ev is not None:  # broadcast already issued beside the projection backward
+                    stream.wait_event(self._marks_ev)
+                    self._marks_ev = None
+                else:
+                    ops.marks_broadcast(self.touched, cur["union_ptrs"], cur["union_multicast"])
                 cur["handle"].barrier(channel=0)  # union marks complete, every rank's private rows final
                 widths = [v.numel() // v.size(0) for v in self.views]
                 ops.rows_pull_marked(cur["union"], widths, self.offsets, self._local_peer_ptrs, cur["peer_ptrs"],
@@ -195,8 +243,6 @@ class FlatGradients:
             else:
                 ops.rows_push_marked(self.touched, self.local_views, self.offsets, cur["peer_ptrs"],
                                      cur["union_ptrs"], cur["multicast"])
-            # reset the other result buffer (rows any rank pushed into two steps ago) for the next step
-            ops.rows_zero_marked(nxt["union"], nxt["views"], clear_marks=True)
             cur["handle"].barrier(channel=0)  # every rank's rows have landed; every 'next' buffer is clean
             self._cur ^= 1
         elif self.sparse and self.module is not None:

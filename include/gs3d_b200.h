@@ -214,14 +214,15 @@ int gs3d_rows_zero_marked(uint8_t *marks, uint32_t N, int n_blocks, const uint64
                           const uint32_t *block_widths_host, int clear_marks, void *stream);
 
 /* Pull form (a sparse NVLS all-reduce; what scales to 8 ranks): gs3d_marks_broadcast sets byte g in
- * every rank's union marks for each marked g; after a cross-rank barrier, gs3d_rows_pull_marked on rank
+ * every rank's union marks for each marked g (multicast_union != NULL: the NVSwitch ORs whole 4-mark words
+ * into all ranks with one multimem.red.or.b32 each; else one byte store per mark and peer); after a cross-rank barrier, gs3d_rows_pull_marked on rank
  * `rank` walks every n_peers-th 512-row chunk of its union marks and, per marked row, reads the sum of
  * ALL ranks' private rows (multimem.ld_reduce.add on multicast_private: reduced inside the NVSwitch;
  * without multicast, peer loads) and stores it into ALL ranks' result buffers (multimem.st on
  * multicast_result; else peer stores).  Private and result buffers share one layout: block s of width
  * block_widths_host[s] starts at float offset block_offsets_host[s].  A second barrier completes it. */
 int gs3d_marks_broadcast(const uint8_t *marks, uint32_t N, const uint64_t *peer_union_ptrs_host, int n_peers,
-                         void *stream);
+                         void *multicast_union, void *stream);
 int gs3d_rows_pull_marked(uint8_t *union_marks, uint32_t N, int n_blocks, const uint32_t *block_widths_host,
                           const uint64_t *block_offsets_host, const uint64_t *peer_private_ptrs_host,
                           const uint64_t *peer_result_ptrs_host, int n_peers, int rank,
