@@ -2,10 +2,11 @@
 (gs/src/bindings.cpp:5-67), same positional signatures, in-place outputs, `None` return -- backed by
 libgs3d_b200.so through the C ABI (include/gs3d_b200.h).
 
-Hot-path bindings are real.  Legacy bindings that no reference caller on the SH path
-uses (RGB v0/v1/v2 kernels, per-tile O(N*tiles) counting, CSR `offset` binning, experimental
-backward variants) raise NotImplementedError naming the supported replacement; nothing falls back
-to a CPU implementation.
+Hot-path bindings are real, and so is the RGB start/end pair behind
+GaussianRenderer.render_aabb_culling (8f rank 2).  The remaining legacy bindings (RGB v0/v1/v2 kernels
+on the CSR `offset` layout -- whose blank-tile fill is commented out in the reference,
+aabb_culling.h:178-182 --, per-tile O(N*tiles) counting, image-level sort) raise NotImplementedError
+naming the supported replacement; nothing falls back to a CPU implementation.
 
 `install()` registers this module as `sys.modules["_gs"]` so the reference's
 `try: import _gs as _backend` (gs/renderer.py:20-23, gs/sh_renderer.py:24-27) picks it up.
@@ -99,6 +100,27 @@ def tile_based_vol_rendering_backward_sh_with_bg(mean, cov, sh_coeffs, alpha, st
                                          pixel_size_y, H, W, C, thresh)
 
 
+def tile_based_vol_rendering_start_end(mean, cov, color, alpha, start, end, gaussian_ids, out, topleft,
+                                       tile_size, n_tiles_h, n_tiles_w, pixel_size_x, pixel_size_y, H, W,
+                                       thresh):
+    """bindings.cpp:29 -> render.cu:399-423 (vol_render.h:716-798)."""
+    ops._chk(color, "color", torch.float32)
+    ops.composite_rgb_forward(_records(mean, cov, alpha), color, start, end, gaussian_ids, out, topleft,
+                              tile_size, n_tiles_h, n_tiles_w, pixel_size_x, pixel_size_y, H, W, thresh,
+                              exact=EXACT_DECISIONS)
+
+
+def tile_based_vol_rendering_backward_start_end(mean, cov, color, alpha, start, end, gaussian_ids, out,
+                                                grad_mean, grad_cov, grad_color, grad_alpha, grad_out,
+                                                topleft, tile_size, n_tiles_h, n_tiles_w, pixel_size_x,
+                                                pixel_size_y, H, W, thresh):
+    """bindings.cpp:31 -> render.cu:425-481 (vol_render.h:800-923)."""
+    ops._chk(color, "color", torch.float32)
+    ops.composite_rgb_backward(_records(mean, cov, alpha), color, start, end, gaussian_ids, out, grad_out,
+                               grad_mean, grad_cov, grad_color, grad_alpha, topleft, tile_size, n_tiles_h,
+                               n_tiles_w, pixel_size_x, pixel_size_y, H, W, thresh, exact=EXACT_DECISIONS)
+
+
 def debug_check_tiledepth(offset_cpu, tiledepth_cpu):
     """gs/src/debug.h:1-32: host-side sortedness check of (tile<<32|depth) keys per tile range."""
     off = offset_cpu.cpu().tolist()
@@ -124,12 +146,10 @@ count_num_gaussians_each_tile_bcircle = _legacy("count_num_gaussians_each_tile_b
 prepare_image_sort = _legacy("prepare_image_sort", "tile_culling_aabb_start_end")
 image_sort = _legacy("image_sort", "tile_culling_aabb_start_end")
 tile_culling_aabb = _legacy("tile_culling_aabb", "tile_culling_aabb_start_end")
-tile_based_vol_rendering = _legacy("tile_based_vol_rendering", "tile_based_vol_rendering_sh")
-tile_based_vol_rendering_v1 = _legacy("tile_based_vol_rendering_v1", "tile_based_vol_rendering_sh")
-tile_based_vol_rendering_v2 = _legacy("tile_based_vol_rendering_v2", "tile_based_vol_rendering_sh")
-tile_based_vol_rendering_backward = _legacy("tile_based_vol_rendering_backward", "tile_based_vol_rendering_backward_sh")
-tile_based_vol_rendering_start_end = _legacy("tile_based_vol_rendering_start_end", "tile_based_vol_rendering_sh")
-tile_based_vol_rendering_backward_start_end = _legacy("tile_based_vol_rendering_backward_start_end", "tile_based_vol_rendering_backward_sh")
+tile_based_vol_rendering = _legacy("tile_based_vol_rendering", "tile_based_vol_rendering_start_end")
+tile_based_vol_rendering_v1 = _legacy("tile_based_vol_rendering_v1", "tile_based_vol_rendering_start_end")
+tile_based_vol_rendering_v2 = _legacy("tile_based_vol_rendering_v2", "tile_based_vol_rendering_start_end")
+tile_based_vol_rendering_backward = _legacy("tile_based_vol_rendering_backward", "tile_based_vol_rendering_backward_start_end")
 # the two experimental backward variants compute the same gradients as the main one
 tile_based_vol_rendering_backward_sh_v1 = tile_based_vol_rendering_backward_sh
 tile_based_vol_rendering_backward_sh_warp_reduce = tile_based_vol_rendering_backward_sh

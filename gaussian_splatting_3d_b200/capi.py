@@ -79,6 +79,10 @@ SIGNATURES = {
     "gs3d_rows_pull_marked": (_i, [_P, _u32, _i, _P, _P, _P, _P, _i, _i, _P, _P, _P]),
     "gs3d_project_backward_fused": (_i, [_u32, _P, _P, _P, _P, _P, _i, _i, _P, _i, _P, _P, _P, _P, _P,
                                          _P, _P, _P, _i, _i, _P]),
+    "gs3d_composite_rgb_forward": (_i, [_u32, _P, _P, _P, _P, _P, _P, _P, _u32, _u32, _u32, _f, _f, _u32, _u32,
+                                        _f, _i, _P]),
+    "gs3d_composite_rgb_backward": (_i, [_u32, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _u32, _u32, _u32,
+                                         _f, _f, _u32, _u32, _f, _i, _P]),
     "gs3d_set_stage_counters": (_i, [_P]),
     "gs3d_adam_step": (_i, [_i, _ADAM, _d, _d, _d, _u32, _i, _P]),
     "gs3d_adc_classify": (_i, [_u32, _P, _P, _i, _f, _P, _i, _f, _P, _P]),

@@ -204,6 +204,19 @@ __device__ __forceinline__ float gaussian_exact(float x, float y, float4 cv) {
   return expf(arg);
 }
 
+// The legacy RGB path evaluates the Gaussian in FP64 (kernel_gaussian_2d, kernels.h:195-214): every operand
+// is widened first, so the only roundings are the double ones and the final cast of exp().
+__device__ __forceinline__ float gaussian_exact_f64(float x, float y, float4 cv) {
+  const double c0 = cv.x, c1 = cv.y, c2 = cv.z, c3 = cv.w;
+  const double det = c0 * c3 - c1 * c2;
+  const double dx = (double)x, dy = (double)y;  // query - mean is an FP32 subtraction promoted afterwards
+  const double tmpx = dx * c3 - dy * c2;
+  const double tmpy = -dx * c1 + dy * c0;
+  double radial = (tmpx * dx + tmpy * dy) / det;
+  if (radial < 0.0) radial = 1000.0;
+  return (float)exp(-0.5 * radial);
+}
+
 // Skip decision for one (pixel, Gaussian) pair (pair_test + pair_decide).  r0 = {m.x, m.y, alpha_, log2 threshold},
 // r1 = {qa, qb, qc, depth}.  Returns true when the pair contributes (alpha_*G >= 1/255) and then
 // G is valid.  Far from the threshold the pre-scaled conic decides alone (no exponential for
@@ -219,7 +232,7 @@ __device__ __forceinline__ float4 pair_test(float px, float py, uint32_t rec_add
   return r0;
 }
 // Part 2, only reached when part 1 did not clearly reject: decide, and produce G.
-template <bool EXACT>
+template <bool EXACT, bool RGB = false>
 __device__ __forceinline__ bool pair_decide(float px, float py, float dead, float pw, float diff,
                                             const float4 r0, uint32_t cov_addr, float &G) {
   if (dead != 0.0f) return false;                // finished pixel that slipped through (non-finite record)
@@ -228,7 +241,8 @@ __device__ __forceinline__ bool pair_decide(float px, float py, float dead, floa
     return true;
   }
   if (EXACT) {
-    const float val = gaussian_exact(px - r0.x, py - r0.y, lds128(cov_addr));
+    const float val = RGB ? gaussian_exact_f64(px - r0.x, py - r0.y, lds128(cov_addr))
+                          : gaussian_exact(px - r0.x, py - r0.y, lds128(cov_addr));
     G = val;
     return !(r0.z * val < MIN_RENDER_ALPHA);
   }
@@ -292,8 +306,11 @@ struct Basis {
 #ifndef GS3D_ABLATE
 #define GS3D_ABLATE 0  // experiment switches (tools/ablate.sh); 0 in every shipped build
 #endif
-template <int CC>
+template <int CC, bool RGB = false>
 __device__ __forceinline__ void sh_colour(uint32_t h_addr, const Basis<CC> &Y, float *y) {
+  if constexpr (RGB) {  // legacy path: the staged row IS the colour (vol_render.h:150-152)
+    y[0] = lds32(h_addr); y[1] = lds32(h_addr + 4); y[2] = lds32(h_addr + 8);
+  } else {
 #pragma unroll
   for (int c = 0; c < 3; ++c) {
     float s;
@@ -331,6 +348,7 @@ __device__ __forceinline__ void sh_colour(uint32_t h_addr, const Basis<CC> &Y, f
     if (isnan(v)) v = 0.0f;
     y[c] = v;
   }
+  }
 }
 
 // ---------------------------------------------------------------- forward
@@ -344,7 +362,7 @@ __device__ __forceinline__ void sh_colour(uint32_t h_addr, const Basis<CC> &Y, f
 #ifndef GS3D_FWD_MINB
 #define GS3D_FWD_MINB 4  // CTAs per SM the forward is compiled for (64 registers)
 #endif
-template <int C, int B, bool EXACT>
+template <int C, int B, bool EXACT, bool RGB = false>
 __global__ void __launch_bounds__(NTHREADS, GS3D_FWD_MINB)
 composite_fwd_kernel(const CompositeParams p) {
   constexpr int CC = C * C;
@@ -381,7 +399,7 @@ composite_fwd_kernel(const CompositeParams p) {
   // pixel corner in camera-plane units (quirk Q4), same expression as vol_render_sh.h:213-214
   const float px = p.topleft[0] + gx * p.psx, py = p.topleft[1] + gy * p.psy;
   Basis<CC> Y;
-  {
+  if constexpr (!RGB) {
     float Yf[CC];
     pixel_basis<C>(p.c2w, px, py, Yf);
     Y.set(Yf);
@@ -433,12 +451,12 @@ composite_fwd_kernel(const CompositeParams p) {
         // image): finished pixels fail the common-case test without a branch of their own
         if (df - dead < -DECISION_MARGIN) continue;  // the common case: clearly below 1/255
         float G;
-        if (pair_decide<EXACT>(px, py, dead, pw, df, r0, rec_a + 48 * u + 32, G)) {
+        if (pair_decide<EXACT, RGB>(px, py, dead, pw, df, r0, rec_a + 48 * u + 32, G)) {
           const float a = r0.z;
           float coeff = (a * T) * G;
-          if (isnan(coeff)) coeff = 0.0f;
+          if (!RGB && isnan(coeff)) coeff = 0.0f;  // vol_render_sh.h:147-150 (the RGB path has no guard)
           float y[3];
-          sh_colour<CC>(sh_a + 4 * SHF * u, Y, y);
+          sh_colour<CC, RGB>(sh_a + 4 * SHF * u, Y, y);
           o0 = fmaf(coeff, y[0], o0);
           o1 = fmaf(coeff, y[1], o1);
           o2 = fmaf(coeff, y[2], o2);
@@ -533,7 +551,7 @@ __device__ __forceinline__ void flush_batch(const CompositeParams &p, float *s_a
 // Same id-ring pipeline as the forward.  The warp-private accumulators are double-buffered: the
 // flush of batch b-1 (sum over warps + global reductions) is issued right after the barrier that
 // starts batch b, so one barrier per batch orders staging, accumulation and flush.
-template <int C, int B, bool EXACT>
+template <int C, int B, bool EXACT, bool RGB = false>
 __global__ void __launch_bounds__(NTHREADS, (B <= 16 ? 3 : 2))
 composite_bwd_kernel(const CompositeParams p) {
   constexpr int CC = C * C;
@@ -570,7 +588,8 @@ composite_bwd_kernel(const CompositeParams p) {
   f32x2 Yt[8];
   {
     float Yf[CC];
-    pixel_basis<C>(p.c2w, px, py, Yf);
+    if constexpr (RGB) Yf[0] = 1.0f;  // colour gradient = plain sum of the per-pixel weights
+    else pixel_basis<C>(p.c2w, px, py, Yf);
     Y.set(Yf);
     constexpr int TS = CC + 1;            // [32][CC+1] per warp; 32*(CC+1) <= B*ROWP for B >= 16
     float *tr = s_acc + warp * 32 * TS;
@@ -654,21 +673,24 @@ composite_bwd_kernel(const CompositeParams p) {
         const float4 r0 = pair_test(px, py, rec_a + 48 * uu, pw, df);
         if (!(df - dead < -DECISION_MARGIN)) {
           float G;
-          if (pair_decide<EXACT>(px, py, dead, pw, df, r0, rec_a + 48 * uu + 32, G)) {
+          if (pair_decide<EXACT, RGB>(px, py, dead, pw, df, r0, rec_a + 48 * uu + 32, G)) {
             contrib = true;
             const float a = r0.z;
             const float aG = a * G;
             float coeff = (a * T) * G;
-            if (isnan(coeff)) coeff = 0.0f;
+            if (!RGB && isnan(coeff)) coeff = 0.0f;
             float y[3];
-            sh_colour<CC>(sh_a + 4 * SHF * uu, Y, y);
+            sh_colour<CC, RGB>(sh_a + 4 * SHF * uu, Y, y);
             f0 = fmaf(-coeff, y[0], f0);
             f1 = fmaf(-coeff, y[1], f1);
             f2 = fmaf(-coeff, y[2], f2);
-            // vol_render_sh.h:328-333
-            w0 = coeff * (y[0] * (1.0f - y[0])) * g0;
-            w1 = coeff * (y[1] * (1.0f - y[1])) * g1;
-            w2 = coeff * (y[2] * (1.0f - y[2])) * g2;
+            if constexpr (RGB) {  // vol_render.h:305-307: grad_color += a T G * grad_out
+              w0 = coeff * g0; w1 = coeff * g1; w2 = coeff * g2;
+            } else {              // vol_render_sh.h:328-333
+              w0 = coeff * (y[0] * (1.0f - y[0])) * g0;
+              w1 = coeff * (y[1] * (1.0f - y[1])) * g1;
+              w2 = coeff * (y[2] * (1.0f - y[2])) * g2;
+            }
             // vol_render_sh.h:336-342
             const float one_m = 1.0f - aG;
             const float inv1m = -rcp_approx(one_m);
@@ -776,12 +798,12 @@ static int env_int(const char *name, int dflt) {
   return v ? atoi(v) : dflt;
 }
 
-template <int C, int B, bool EXACT>
+template <int C, int B, bool EXACT, bool RGB = false>
 static int launch_fwd_t(const CompositeParams &p, uint32_t n_tiles, cudaStream_t st) {
   size_t sm = fwd_smem<C, B>();
-  GS3D_CUDA(cudaFuncSetAttribute(composite_fwd_kernel<C, B, EXACT>,
+  GS3D_CUDA(cudaFuncSetAttribute(composite_fwd_kernel<C, B, EXACT, RGB>,
                                  cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
-  composite_fwd_kernel<C, B, EXACT><<<n_tiles, NTHREADS, sm, st>>>(p);
+  composite_fwd_kernel<C, B, EXACT, RGB><<<n_tiles, NTHREADS, sm, st>>>(p);
   GS3D_LAUNCH_CHECK();
   return GS3D_OK;
 }
@@ -790,12 +812,12 @@ static int launch_fwd(const CompositeParams &p, uint32_t n_tiles, cudaStream_t s
   return p.exact ? launch_fwd_t<C, FWD_B, true>(p, n_tiles, st)
                  : launch_fwd_t<C, FWD_B, false>(p, n_tiles, st);
 }
-template <int C, int B, bool EXACT>
+template <int C, int B, bool EXACT, bool RGB = false>
 static int launch_bwd_t(const CompositeParams &p, uint32_t n_tiles, cudaStream_t st) {
   size_t sm = bwd_smem<C, B>();
-  GS3D_CUDA(cudaFuncSetAttribute(composite_bwd_kernel<C, B, EXACT>,
+  GS3D_CUDA(cudaFuncSetAttribute(composite_bwd_kernel<C, B, EXACT, RGB>,
                                  cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
-  composite_bwd_kernel<C, B, EXACT><<<n_tiles, NTHREADS, sm, st>>>(p);
+  composite_bwd_kernel<C, B, EXACT, RGB><<<n_tiles, NTHREADS, sm, st>>>(p);
   GS3D_LAUNCH_CHECK();
   return GS3D_OK;
 }
@@ -932,6 +954,69 @@ int gs3d_composite_sh_backward(uint32_t M, const float *records, const float *sh
                                           gsh_stride_g, gsh_stride_c, grad_alpha, topleft, c2w, tile_size,
                                           n_tiles_h, n_tiles_w, pixel_size_x, pixel_size_y, H, W, C,
                                           thresh, exact_decisions, nullptr, 0, nullptr, nullptr, stream);
+}
+
+// ---- legacy RGB path: tile_based_vol_rendering_start_end{,_backward}, bindings.cpp:29-33 /
+// render.cu / vol_render.h:716-923.  Same kernels, RGB mode: the staged row is the colour itself, the
+// near-threshold decisions use the reference's FP64 Gaussian.
+
+static int rgb_params(CompositeParams &p, const float *records, const float *color, const int32_t *start,
+                      const int32_t *end, const int32_t *gaussian_ids, const float *topleft, uint32_t tile_size,
+                      uint32_t n_tiles_h, uint32_t n_tiles_w, float psx, float psy, uint32_t H, uint32_t W,
+                      float thresh, int exact) {
+  GS3D_REQUIRE(tile_size == TILE, GS3D_EUNSUPPORTED, "compositing kernels support tile_size 16 only (got %u)",
+               tile_size);
+  GS3D_REQUIRE(start && end && topleft && color, GS3D_EINVAL, "composite_rgb: null argument");
+  GS3D_REQUIRE(aligned16(records), GS3D_EINVAL, "records must be 16-byte aligned");
+  p.records = reinterpret_cast<const float4 *>(records);
+  p.sh = color; p.sh_sg = 3; p.sh_sc = 1; p.sh_vec = 0;
+  p.start = start; p.end = end; p.ids = gaussian_ids; p.topleft = topleft; p.c2w = nullptr;
+  p.ntw = n_tiles_w; p.nth = n_tiles_h; p.psx = psx; p.psy = psy; p.H = H; p.W = W; p.thresh = thresh;
+  p.exact = exact;
+  p.stats = g_stage_counters;
+  return GS3D_OK;
+}
+
+int gs3d_composite_rgb_forward(uint32_t M, const float *records, const float *color, const int32_t *start,
+                               const int32_t *end, const int32_t *gaussian_ids, float *out, const float *topleft,
+                               uint32_t tile_size, uint32_t n_tiles_h, uint32_t n_tiles_w, float pixel_size_x,
+                               float pixel_size_y, uint32_t H, uint32_t W, float thresh, int exact_decisions,
+                               void *stream) {
+  (void)M;
+  const uint32_t n_tiles = n_tiles_h * n_tiles_w;
+  if (n_tiles == 0 || H == 0 || W == 0) return GS3D_OK;
+  GS3D_REQUIRE(out, GS3D_EINVAL, "composite_rgb_forward: out is null");
+  CompositeParams p = {};
+  int rc = rgb_params(p, records, color, start, end, gaussian_ids, topleft, tile_size, n_tiles_h, n_tiles_w,
+                      pixel_size_x, pixel_size_y, H, W, thresh, exact_decisions);
+  if (rc) return rc;
+  p.out = out;
+  cudaStream_t st = as_stream(stream);
+  return exact_decisions ? launch_fwd_t<1, FWD_B, true, true>(p, n_tiles, st)
+                         : launch_fwd_t<1, FWD_B, false, true>(p, n_tiles, st);
+}
+
+int gs3d_composite_rgb_backward(uint32_t M, const float *records, const float *color, const int32_t *start,
+                                const int32_t *end, const int32_t *gaussian_ids, const float *out,
+                                const float *grad_out, float *grad_mean2d, float *grad_cov2d, float *grad_color,
+                                float *grad_alpha, const float *topleft, uint32_t tile_size, uint32_t n_tiles_h,
+                                uint32_t n_tiles_w, float pixel_size_x, float pixel_size_y, uint32_t H, uint32_t W,
+                                float thresh, int exact_decisions, void *stream) {
+  (void)M;
+  const uint32_t n_tiles = n_tiles_h * n_tiles_w;
+  if (n_tiles == 0 || H == 0 || W == 0) return GS3D_OK;
+  GS3D_REQUIRE(out && grad_out && grad_mean2d && grad_cov2d && grad_color && grad_alpha, GS3D_EINVAL,
+               "composite_rgb_backward: null argument");
+  CompositeParams p = {};
+  int rc = rgb_params(p, records, color, start, end, gaussian_ids, topleft, tile_size, n_tiles_h, n_tiles_w,
+                      pixel_size_x, pixel_size_y, H, W, thresh, exact_decisions);
+  if (rc) return rc;
+  p.out_saved = out; p.grad_out = grad_out;
+  p.g_mean = grad_mean2d; p.g_cov = grad_cov2d; p.g_sh = grad_color; p.g_alpha = grad_alpha;
+  p.gsh_sg = 3; p.gsh_sc = 1; p.gsh_vec = 0;
+  cudaStream_t st = as_stream(stream);
+  return exact_decisions ? launch_bwd_t<1, 16, true, true>(p, n_tiles, st)
+                         : launch_bwd_t<1, 16, false, true>(p, n_tiles, st);
 }
 
 }  // extern "C"

@@ -9,9 +9,11 @@ Differences in mechanism, not in results:
     instead of ~25 ATen launches + 2 bmm + 2 einsum and their autograd graph.
   * the render Functions keep the reference's contract (caller-visible tensors, in-place kernels)
     but run on the current stream with no cudaProfilerStart/Stop brackets.
-The legacy RGB Functions `render` / `render_start_end` and the `Renderer` / `GaussianRenderer`
-classes (renderer.py:33-362, 422-670, 1002-1549) are outside the SH hot path
-and raise NotImplementedError.
+Legacy RGB path: `render_start_end` (renderer.py:536-671) and
+`GaussianRenderer` with `tile_culling_type: aabb` (renderer.py:1002-1549; forward =
+render_aabb_culling :1219-1305) run on the same kernels in RGB mode.  The older `render` Function on the
+CSR `offset` layout and `render_lecacy` stay NotImplementedError (deprecated in the reference itself:
+the blank-tile offset fill is commented out, aabb_culling.h:178-182).
 """
 import torch
 
@@ -136,6 +138,40 @@ def render_sh_bg(mean, cov, sh_coeffs, alpha, start, end, gaussian_ids, topleft,
                             thresh, bg_rgb)
 
 
+class _render_start_end(torch.autograd.Function):
+    """renderer.py:536-671: RGB compositing over (start, end) tile ranges through the `_gs` bindings."""
+
+    @staticmethod
+    def forward(ctx, mean, cov, color, alpha, start, end, gaussian_ids, topleft, tile_size, n_tiles_h,
+                n_tiles_w, pixel_size_x, pixel_size_y, H, W, thresh):
+        out = torch.zeros([H * W * 3], dtype=torch.float32, device=mean.device)
+        mean, cov, color, alpha = mean.contiguous(), cov.contiguous(), color.contiguous(), alpha.contiguous()
+        consts = (tile_size, n_tiles_h, n_tiles_w, pixel_size_x, pixel_size_y, H, W, thresh)
+        _backend.tile_based_vol_rendering_start_end(mean, cov, color, alpha, start, end, gaussian_ids, out,
+                                                    topleft, *consts)
+        ctx.save_for_backward(mean, cov, color, alpha, start, end, gaussian_ids, out, topleft)
+        ctx.const = consts
+        return out
+
+    @staticmethod
+    def backward(ctx, grad):
+        mean, cov, color, alpha, start, end, gaussian_ids, out, topleft = ctx.saved_tensors
+        grad_mean = torch.zeros_like(mean)
+        grad_cov = torch.zeros_like(cov)
+        grad_color = torch.zeros_like(color)
+        grad_alpha = torch.zeros_like(alpha)
+        _backend.tile_based_vol_rendering_backward_start_end(
+            mean, cov, color, alpha, start, end, gaussian_ids, out, grad_mean, grad_cov, grad_color,
+            grad_alpha, grad.contiguous(), topleft, *ctx.const)
+        return (grad_mean, grad_cov, grad_color, grad_alpha) + (None,) * 12
+
+
+def render_start_end(mean, cov, color, alpha, start, end, gaussian_ids, topleft, tile_size, n_tiles_h,
+                     n_tiles_w, pixel_size_x, pixel_size_y, H, W, thresh):
+    return _render_start_end.apply(mean, cov, color, alpha, start, end, gaussian_ids, topleft, tile_size,
+                                   n_tiles_h, n_tiles_w, pixel_size_x, pixel_size_y, H, W, thresh)
+
+
 # ---------------------------------------------------------------- fused whole-path Function
 
 
@@ -174,10 +210,16 @@ class _splat_sh(torch.autograd.Function):
         bg = state.get("bg_rgb")
         out = torch.zeros(H * W * 3, dtype=torch.float32, device=dev) if bg is None else \
             torch.empty(H * W * 3, dtype=torch.float32, device=dev)
-        sh_c = sh_coeffs if sh_coeffs.stride(2) == 1 else sh_coeffs.contiguous()
-        ops.composite_sh_forward(k1["records"], sh_c, start, end, ids, out, topleft, c2w_c, tile,
-                                 nth, ntw, psx, psy, H, W, C, state["T_thresh"], bg_rgb=bg,
-                                 exact=state.get("exact", True))
+        rgb = bool(state.get("rgb"))  # legacy GaussianRenderer: `sh_coeffs` is the activated colour [N,3]
+        if rgb:
+            sh_c = sh_coeffs.contiguous()
+            ops.composite_rgb_forward(k1["records"], sh_c, start, end, ids, out, topleft, tile, nth, ntw, psx,
+                                      psy, H, W, state["T_thresh"], exact=state.get("exact", True))
+        else:
+            sh_c = sh_coeffs if sh_coeffs.stride(2) == 1 else sh_coeffs.contiguous()
+            ops.composite_sh_forward(k1["records"], sh_c, start, end, ids, out, topleft, c2w_c, tile,
+                                     nth, ntw, psx, psy, H, W, C, state["T_thresh"], bg_rgb=bg,
+                                     exact=state.get("exact", True))
         ctx.save_for_backward(mean_c, qvec_c, svec_c, sh_c, alpha_c, c2w_c, k1["records"], k1["mask"],
                               ids, start, end, out, topleft)
         ctx.meta = (tile, nth, ntw, psx, psy, H, W, C, state["T_thresh"], state["svec_act"],
@@ -207,12 +249,17 @@ class _splat_sh(torch.autograd.Function):
         else:
             g_sh = torch.zeros(sh.shape, dtype=torch.float32, device=dev)
             leaf_out = None
-        ops.composite_sh_backward(records, sh, start, end, ids, out, grad_out.contiguous().view(-1),
-                                  g_mean2d, g_cov, g_sh, g_alpha, topleft, c2w, tile, nth, ntw, psx,
-                                  psy, H, W, C, thresh, exact=exact,
-                                  peer_ptrs=bufs.get("sh_peer_ptrs") if bufs else None,
-                                  multicast_ptr=bufs.get("sh_multicast_ptr") if bufs else None,
-                                  touched=bufs.get("touched") if bufs else None)
+        if st.get("rgb"):
+            ops.composite_rgb_backward(records, sh, start, end, ids, out, grad_out.contiguous().view(-1),
+                                       g_mean2d, g_cov, g_sh, g_alpha, topleft, tile, nth, ntw, psx, psy,
+                                       H, W, thresh, exact=exact)
+        else:
+            ops.composite_sh_backward(records, sh, start, end, ids, out, grad_out.contiguous().view(-1),
+                                      g_mean2d, g_cov, g_sh, g_alpha, topleft, c2w, tile, nth, ntw, psx,
+                                      psy, H, W, C, thresh, exact=exact,
+                                      peer_ptrs=bufs.get("sh_peer_ptrs") if bufs else None,
+                                      multicast_ptr=bufs.get("sh_multicast_ptr") if bufs else None,
+                                      touched=bufs.get("touched") if bufs else None)
         if bufs is not None and bufs.get("after_composite_backward") is not None:
             bufs["after_composite_backward"]()  # e.g. the data-parallel mark broadcast, on a side stream
         gm, gq, gs, ga = ops.project_backward_fused(
@@ -239,14 +286,206 @@ def _legacy(name):
 
 
 render = _legacy("render")
-render_start_end = _legacy("render_start_end")
 
 
 class GaussianRenderer(torch.nn.Module):
-    def __init__(self, *a, **k):
+    """The RGB model module of the reference (renderer.py:1002-1549) on the B200 kernels: parameters
+    `mean, qvec, svec_before_activation, color_before_activation, alpha_before_activation`, properties
+    `svec, color, alpha`, `forward(c2w, camera_info) -> [H,W,3]` (= render_aabb_culling, :1219-1305),
+    `split_gaussians` (:1325-1405, hot = ||mean.grad|| > pos_grad_thresh), `remove_low_alpha_gaussians`,
+    `reset_alpha`, `adaptive_control` (:1437-1444), `save` / `load`, `log*`.
+
+    Underneath, forward is the fused whole-path Function of the SH model in RGB mode (cull + project +
+    rects in one kernel, radix binning, compositing of the activated colour); the colour activation stays
+    a torch op so any `color_act` of utils/activations.py works."""
+
+    _NAMES = ("mean", "qvec", "svec_before_activation", "color_before_activation", "alpha_before_activation")
+
+    def __init__(self, cfg, pts, rgb):
         super().__init__()
-        raise NotImplementedError("GaussianRenderer (legacy RGB module, renderer.py:1002-1549) is "
-                                  "outside the SH hot path; use gs.sh_renderer.SHRenderer.")
+        from ..utils.activations import activations, inv_activations
+
+        self.device = cfg.device
+        self.cfg = cfg
+        self.N = pts.shape[0]
+        self.svec_act, self.color_act, self.alpha_act = (activations[cfg.svec_act], activations[cfg.color_act],
+                                                         activations[cfg.alpha_act])
+        self.svec_inv_act, self.color_inv_act, self.alpha_inv_act = (
+            inv_activations[cfg.svec_act], inv_activations[cfg.color_act], inv_activations[cfg.alpha_act])
+        codes = {"exp": ("exp", 1), "sigmoid": ("sigmoid", 1), "nothing": (None, 0)}
+        if cfg.svec_act not in ("exp", "nothing") or cfg.alpha_act not in ("sigmoid", "nothing"):
+            raise NotImplementedError("fused kernels support svec_act in {exp, nothing} and alpha_act in "
+                                      "{sigmoid, nothing}")
+        self._svec_code, self._alpha_code = codes[cfg.svec_act][1], codes[cfg.alpha_act][1]
+        dev = cfg.device
+        self.mean = torch.nn.Parameter(pts.to(dev))
+        qvec = torch.zeros([self.N, 4], device=dev)
+        qvec[..., 0] = 1.0
+        self.qvec = torch.nn.Parameter(qvec)
+        self.svec_before_activation = torch.nn.Parameter(
+            torch.full([self.N, 3], float(self.svec_inv_act(cfg.svec_init)), device=dev))
+        self.color_before_activation = torch.nn.Parameter(self.color_inv_act(rgb.to(dev)))
+        self.alpha_before_activation = torch.nn.Parameter(
+            torch.full([self.N], float(self.alpha_inv_act(cfg.alpha_init)), device=dev))
+        self.depth = self.radius = None
+        self.total_dub_gaussians = 0
+        self.set_cfg(cfg)
+
+    def set_cfg(self, cfg):
+        g = cfg.get
+        self.tile_size = cfg.tile_size
+        self.frustum_culling_radius = cfg.frustum_culling_radius
+        self.tile_culling_type = cfg.tile_culling_type
+        self.tile_culling_radius = cfg.tile_culling_radius
+        self.tile_culling_thresh = g("tile_culling_thresh", 0.01)
+        self.T_thresh = cfg.T_thresh
+        self.adaptive_control_iteration = cfg.adaptive_control_iteration
+        self.pos_grad_thresh = cfg.pos_grad_thresh
+        self.split_scale_thresh = cfg.split_scale_thresh
+        self.scale_shrink_factor = cfg.scale_shrink_factor
+        self.alpha_reset_period = cfg.alpha_reset_period
+        self.alpha_reset_val = cfg.alpha_reset_val
+        self.alpha_thresh = cfg.alpha_thresh
+        self.exact_decisions = g("exact_decisions", True)
+
+    @property
+    def svec(self):
+        return self.svec_act(self.svec_before_activation)
+
+    @property
+    def color(self):
+        return self.color_act(self.color_before_activation)
+
+    @property
+    def alpha(self):
+        return self.alpha_act(self.alpha_before_activation)
+
+    def render_aabb_culling(self, c2w, camera_info):
+        state = {
+            "camera_info": camera_info, "tile_size": self.tile_size, "C": 1, "rgb": True,
+            "svec_act": self._svec_code, "alpha_act": self._alpha_code,
+            "frustum_radius": self.frustum_culling_radius, "skip_frustum_culling": False,
+            "tile_D": self.tile_culling_radius, "T_thresh": self.T_thresh, "detach_depth": True,
+            "cnt": None, "bg_rgb": None, "exact": self.exact_decisions, "adc_acc": None, "adc_mode": 0,
+            "grad_buffers": None,
+        }
+        out = splat_sh(self.mean, self.qvec, self.svec_before_activation, self.color,
+                       self.alpha_before_activation, c2w, state)
+        self.total_dub_gaussians = state["n_dub"]
+        self.depth = state["out_k1"]["depth"]
+        self.radius = None
+        return out.view(camera_info.h, camera_info.w, 3)
+
+    def render_lecacy(self, c2w, camera_info):
+        raise NotImplementedError("GaussianRenderer.render_lecacy (renderer.py:1057-1217, image-level sort on "
+                                  "bounding circles) is deprecated in the reference; use tile_culling_type 'aabb'")
+
+    def forward(self, c2w, camera_info):
+        if self.cfg.tile_culling_type == "aabb":
+            return self.render_aabb_culling(c2w, camera_info)
+        return self.render_lecacy(c2w, camera_info)
+
+    # ------------------------------------------------------------------ adaptive density control
+    def _params(self):
+        return [getattr(self, n).data for n in self._NAMES]
+
+    def _set(self, new):
+        for n, t in zip(self._NAMES, new):
+            setattr(self, n, torch.nn.Parameter(t))
+        self.N = self.mean.shape[0]
+
+    def _move(self, plan, noise=None):
+        m, q, s, c, a = self._params()
+        return ops.adc_apply(plan, m, q, s, c, a, self._svec_code, self.scale_shrink_factor, noise)
+
+    def split_gaussians(self):
+        """renderer.py:1325-1405 (same row order as SHRenderer.split_gaussians)."""
+        assert self.mean.grad is not None, "mean.grad is None"
+        hot = self.mean.grad.norm(dim=-1)
+        cls = ops.adc_classify(hot, None, "max", self.pos_grad_thresh, self.svec_before_activation.data,
+                               self._svec_code, self.split_scale_thresh)
+        plan, (n_stay, num_clone, num_split) = ops.adc_plan(cls)
+        print(f"Splitting Gaussians: num_split {num_split} num_clone {num_clone}")
+        noise = torch.randn(num_split * 2, 3, device=self.mean.device)
+        self._set(self._move(plan, noise))
+        print(f"num gaussians: {self.N}")
+
+    def remove_low_alpha_gaussians(self):
+        before = self.N
+        cls = ops.adc_classify_alpha(self.alpha_before_activation.data, self._alpha_code, self.alpha_thresh)
+        plan, _ = ops.adc_plan(cls)
+        self._set(self._move(plan))
+        print(f"remove_low_alpha_gaussians: removed {before - self.N}, remaining {self.N}")
+
+    def reset_alpha(self):
+        self.alpha_before_activation.data.fill_(self.alpha_inv_act(self.alpha_reset_val))
+
+    def adaptive_control(self, iteration):
+        """renderer.py:1437-1444."""
+        if step_check(iteration + 1, self.alpha_reset_period):
+            self.remove_low_alpha_gaussians()
+        if step_check(iteration, self.alpha_reset_period, run_at_zero=False):
+            self.reset_alpha()
+        if step_check(iteration, self.adaptive_control_iteration):
+            self.split_gaussians()
+
+    # ------------------------------------------------------------------ logging (renderer.py:1455-1526)
+    def log_n_gaussian_dub(self, writer, step):
+        writer.add_scalar("n_gaussian_dub", self.total_dub_gaussians, step)
+
+    @torch.no_grad()
+    def log_grad_bounds(self, writer, step):
+        if self.mean.grad is None:
+            return
+        for tag, p in (("mean", self.mean), ("qvec", self.qvec), ("svec", self.svec_before_activation),
+                       ("color", self.color_before_activation), ("alpha", self.alpha_before_activation)):
+            if p.grad is not None:
+                writer.add_scalar(f"grad_bounds/{tag}_max", p.grad.max(), step)
+                writer.add_scalar(f"grad_bounds/{tag}_min", p.grad.min(), step)
+
+    @torch.no_grad()
+    def log_info(self, writer, step):
+        for tag, t in (("mean", self.mean), ("qvec", self.qvec), ("svec", self.svec), ("color", self.color),
+                       ("alpha", self.alpha)):
+            writer.add_scalar(f"info/{tag}_mean", t.abs().mean(), step)
+
+    @torch.no_grad()
+    def log_bounds(self, writer, step):
+        for tag, t in (("mean", self.mean), ("qvec", self.qvec), ("svec", self.svec), ("color", self.color),
+                       ("alpha", self.alpha)):
+            writer.add_scalar(f"bounds/{tag}_max", t.max(), step)
+            writer.add_scalar(f"bounds/{tag}_min", t.min(), step)
+
+    @torch.no_grad()
+    def log_depth_and_radius(self, writer, step):
+        for tag, t in (("depth", self.depth), ("radius", self.radius)):
+            if t is not None:
+                writer.add_scalar(f"bounds/{tag}_max", t.max(), step)
+                writer.add_scalar(f"bounds/{tag}_min", t.min(), step)
+                writer.add_scalar(f"bounds/{tag}_mean", t.mean(), step)
+
+    def log(self, writer, step):
+        for fn in (self.log_depth_and_radius, self.log_bounds, self.log_info, self.log_grad_bounds,
+                   self.log_n_gaussian_dub):
+            fn(writer, step)
+
+    # ------------------------------------------------------------------ checkpoint (renderer.py:1531-1549)
+    def save(self, path):
+        from pathlib import Path
+
+        Path(path).parent.mkdir(parents=True, exist_ok=True)
+        state = {n: getattr(self, n).data for n in self._NAMES}
+        state["N"], state["cfg"] = self.N, self.cfg
+        torch.save(state, path)
+
+    @classmethod
+    def load(cls, path, cfg=None):
+        state = torch.load(path, weights_only=False)
+        cfg = cfg if cfg is not None else state["cfg"]
+        r = cls(cfg, state["mean"], torch.full_like(state["mean"], 0.5))
+        r._set([state[n].to(cfg.device) for n in cls._NAMES])
+        assert r.N == state["N"]
+        return r
 
 
 Renderer = GaussianRenderer

@@ -385,6 +385,45 @@ def clip_rects_to_rows(aabb_topleft, aabb_bottomright, depth, row_begin, row_end
     return tl[:m], br[:m], dp[:m], idx[:m], int(counts[1])
 
 
+# ---------------------------------------------------------------- legacy RGB path (8f rank 2)
+def composite_rgb_forward(records, color, start, end, gaussian_ids, out, topleft, tile_size, n_tiles_h,
+                          n_tiles_w, pixel_size_x, pixel_size_y, H, W, thresh, exact=True):
+    """tile_based_vol_rendering_start_end (vol_render.h:716-798) on staging records; color [M,3]."""
+    _chk(records, "records", _F32)
+    for t, n in ((start, "start"), (end, "end"), (gaussian_ids, "gaussian_ids")):
+        _chk(t, n, _I32)
+    for t, n in ((color, "color"), (out, "out"), (topleft, "topleft")):
+        _chk(t, n, _F32)
+    if color.numel() != 3 * records.size(0):
+        raise RuntimeError("color must be [M,3]")
+    if out.numel() < H * W * 3:
+        raise RuntimeError("out must have H*W*3 elements")
+    check(capi.lib.gs3d_composite_rgb_forward(
+        records.size(0), ptr(records), ptr(color), ptr(start), ptr(end), ptr(gaussian_ids), ptr(out),
+        ptr(topleft), int(tile_size), int(n_tiles_h), int(n_tiles_w), float(pixel_size_x), float(pixel_size_y),
+        int(H), int(W), float(thresh), 1 if exact else 0, _stream(out)), "tile_based_vol_rendering_start_end")
+
+
+def composite_rgb_backward(records, color, start, end, gaussian_ids, out, grad_out, grad_mean, grad_cov,
+                           grad_color, grad_alpha, topleft, tile_size, n_tiles_h, n_tiles_w, pixel_size_x,
+                           pixel_size_y, H, W, thresh, exact=True):
+    """tile_based_vol_rendering_backward_start_end (vol_render.h:800-923); gradients accumulated."""
+    _chk(records, "records", _F32)
+    for t, n in ((start, "start"), (end, "end"), (gaussian_ids, "gaussian_ids")):
+        _chk(t, n, _I32)
+    for t, n in ((color, "color"), (out, "out"), (grad_out, "grad_out"), (grad_mean, "grad_mean"),
+                 (grad_cov, "grad_cov"), (grad_color, "grad_color"), (grad_alpha, "grad_alpha"),
+                 (topleft, "topleft")):
+        _chk(t, n, _F32)
+    if color.numel() != 3 * records.size(0) or grad_color.numel() != color.numel():
+        raise RuntimeError("color / grad_color must be [M,3]")
+    check(capi.lib.gs3d_composite_rgb_backward(
+        records.size(0), ptr(records), ptr(color), ptr(start), ptr(end), ptr(gaussian_ids), ptr(out),
+        ptr(grad_out), ptr(grad_mean), ptr(grad_cov), ptr(grad_color), ptr(grad_alpha), ptr(topleft),
+        int(tile_size), int(n_tiles_h), int(n_tiles_w), float(pixel_size_x), float(pixel_size_y), int(H), int(W),
+        float(thresh), 1 if exact else 0, _stream(out)), "tile_based_vol_rendering_backward_start_end")
+
+
 # ---------------------------------------------------------------- measurement aid
 def set_stage_counters(counters):
     """counters: int64 [2] CUDA tensor (zeroed) or None; see gs3d_set_stage_counters."""

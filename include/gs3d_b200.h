@@ -228,6 +228,26 @@ int gs3d_rows_pull_marked(uint8_t *union_marks, uint32_t N, int n_blocks, const 
                           const uint64_t *peer_result_ptrs_host, int n_peers, int rank,
                           const void *multicast_private, void *multicast_result, void *stream);
 
+/* ---- legacy RGB path: tile_based_vol_rendering_start_end and its backward,
+ * bindings.cpp:29-33 / render.cu:399-481 / vol_render.h:716-923 (batch loops :169-250, :252-352), behind
+ * gs/renderer.py:536-671 `render_start_end` and GaussianRenderer.render_aabb_culling (:1219-1305).
+ * Same kernels as the SH path in RGB mode: color [M,3] is composited as it is (no SH basis, no sigmoid,
+ * no NaN guards), grad_color += a*T*G*grad_out, and -- exact_decisions != 0 -- skip decisions near the
+ * 1/255 threshold are taken with the reference's FP64 Gaussian (kernel_gaussian_2d, kernels.h:195-214).
+ * records as for the SH entry points (gs3d_pack_records / gs3d_project_cull_fused); out pre-zeroed by the
+ * caller (renderer.py:558); gradients are ACCUMULATED into pre-zeroed buffers (renderer.py:609-612). */
+int gs3d_composite_rgb_forward(uint32_t M, const float *records, const float *color, const int32_t *start,
+                               const int32_t *end, const int32_t *gaussian_ids, float *out, const float *topleft,
+                               uint32_t tile_size, uint32_t n_tiles_h, uint32_t n_tiles_w, float pixel_size_x,
+                               float pixel_size_y, uint32_t H, uint32_t W, float thresh, int exact_decisions,
+                               void *stream);
+int gs3d_composite_rgb_backward(uint32_t M, const float *records, const float *color, const int32_t *start,
+                                const int32_t *end, const int32_t *gaussian_ids, const float *out,
+                                const float *grad_out, float *grad_mean2d, float *grad_cov2d, float *grad_color,
+                                float *grad_alpha, const float *topleft, uint32_t tile_size, uint32_t n_tiles_h,
+                                uint32_t n_tiles_w, float pixel_size_x, float pixel_size_y, uint32_t H, uint32_t W,
+                                float thresh, int exact_decisions, void *stream);
+
 /* ---- a9 + a10 fused: chain rule from (grad_mean2d, grad_cov2d, grad_alpha) to the leaf
  * parameters through projection (Q6) and the activations (sh_renderer.py:318-324), for the
  * Gaussians with mask != 0 (others get zero gradient; mask NULL = all), plus the ADC accumulator

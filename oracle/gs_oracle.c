@@ -389,3 +389,132 @@ void gso_tile_based_vol_rendering_backward_sh(
   free(acc);
 }
 
+
+/* ---------------------------------------------------------------- legacy RGB compositing (8f rank 2) */
+
+/* kernels.h:195-214 kernel_gaussian_2d: every operand widened to FP64 first (the query - mean
+ * subtraction is FP32, then promoted), exp in double, one final cast. */
+float gso_gaussian_2d_f64(const float *mean, const float *cov, const float *query) {
+  double c0 = cov[0], c1 = cov[1], c2 = cov[2], c3 = cov[3];
+  double det = c0 * c3 - c1 * c2;
+  double x = (double)(float)(query[0] - mean[0]);
+  double y = (double)(float)(query[1] - mean[1]);
+  double tmpx = x * c3 - y * c2;
+  double tmpy = -x * c1 + y * c0;
+  double radial = tmpx * x + tmpy * y;
+  radial /= det;
+  if (radial < 0.0) radial = 1000.0;
+  return (float)exp(-0.5 * radial);
+}
+
+/* vol_render.h:716-798 (entry) + :169-250 (batch loop, same arithmetic as :87-167).  Caller pre-zeroes
+ * out (renderer.py:558).  margin: as in the SH oracle. */
+void gso_tile_based_vol_rendering_start_end(
+    const float *mean, const float *cov, const float *color, const float *alpha, const int32_t *start,
+    const int32_t *end, const int32_t *gaussian_ids, float *out_rgb, const float *topleft,
+    uint32_t tile_size, uint32_t n_tiles_h, uint32_t n_tiles_w, float pixel_size_x, float pixel_size_y,
+    uint32_t H, uint32_t W, float thresh, float *margin) {
+#pragma omp parallel for schedule(dynamic, 1)
+  for (int64_t tile_id = 0; tile_id < (int64_t)n_tiles_h * n_tiles_w; ++tile_id) {
+    uint32_t by = (uint32_t)(tile_id / n_tiles_w), bx = (uint32_t)(tile_id % n_tiles_w);
+    if (start[tile_id] == -1) continue;
+    int n_this = end[tile_id] - start[tile_id];
+    if (n_this == 0) continue;
+    const int32_t *ids = gaussian_ids + start[tile_id];
+    for (uint32_t ly = 0; ly < tile_size; ++ly)
+      for (uint32_t lx = 0; lx < tile_size; ++lx) {
+        uint32_t gy = by * tile_size + ly, gx = bx * tile_size + lx;
+        if (gy >= H || gx >= W) continue;
+        uint64_t pix = (uint64_t)gy * W + gx;
+        float pos[2] = {topleft[0] + gx * pixel_size_x, topleft[1] + gy * pixel_size_y};
+        float out[3] = {0.0f, 0.0f, 0.0f};
+        float cum_alpha = 1.0f, mrg = 1.0f;
+        for (int i = 0; i < n_this; ++i) {
+          if (cum_alpha < thresh) break;
+          int32_t g = ids[i];
+          float alpha_ = fminf(alpha[g], 0.99f);
+          float coeff = alpha_ * cum_alpha;
+          float val = gso_gaussian_2d_f64(mean + 2 * (int64_t)g, cov + 4 * (int64_t)g, pos);
+          coeff *= val;
+          float m = fabsf(alpha_ * val * 255.0f - 1.0f);
+          if (m < mrg) mrg = m;
+          if (alpha_ * val < GSO_MIN_RENDER_ALPHA) continue;
+          out[0] += color[3 * (int64_t)g + 0] * coeff;
+          out[1] += color[3 * (int64_t)g + 1] * coeff;
+          out[2] += color[3 * (int64_t)g + 2] * coeff;
+          cum_alpha *= (1 - alpha_ * val);
+        }
+        out_rgb[3 * pix + 0] = out[0];
+        out_rgb[3 * pix + 1] = out[1];
+        out_rgb[3 * pix + 2] = out[2];
+        if (margin) margin[pix] = mrg;
+      }
+  }
+}
+
+/* vol_render.h:800-923 (entry) + :252-352 (batch loop): grad_color += a*T*G*grad_out; partial_aG is a
+ * DOUBLE accumulator there (:309-325); kernel_gaussian_2d_backward and grad_alpha take its float cast.
+ * FP32 addends summed in FP64 and rounded once, like the SH oracle. */
+void gso_tile_based_vol_rendering_backward_start_end(
+    uint32_t N, const float *mean, const float *cov, const float *color, const float *alpha,
+    const int32_t *start, const int32_t *end, const int32_t *gaussian_ids, const float *out_rgb,
+    float *grad_mean, float *grad_cov, float *grad_color, float *grad_alpha, const float *grad_out_rgb,
+    const float *topleft, uint32_t tile_size, uint32_t n_tiles_h, uint32_t n_tiles_w, float pixel_size_x,
+    float pixel_size_y, uint32_t H, uint32_t W, float thresh) {
+  const uint32_t row = 10;
+  double *acc = (double *)calloc((size_t)N * row, sizeof(double));
+#pragma omp parallel for schedule(dynamic, 1)
+  for (int64_t tile_id = 0; tile_id < (int64_t)n_tiles_h * n_tiles_w; ++tile_id) {
+    uint32_t by = (uint32_t)(tile_id / n_tiles_w), bx = (uint32_t)(tile_id % n_tiles_w);
+    if (start[tile_id] == -1) continue;
+    int n_this = end[tile_id] - start[tile_id];
+    if (n_this == 0) continue;
+    const int32_t *ids = gaussian_ids + start[tile_id];
+    for (uint32_t ly = 0; ly < tile_size; ++ly)
+      for (uint32_t lx = 0; lx < tile_size; ++lx) {
+        uint32_t gy = by * tile_size + ly, gx = bx * tile_size + lx;
+        if (gy >= H || gx >= W) continue;
+        uint64_t pix = (uint64_t)gy * W + gx;
+        float pos[2] = {topleft[0] + gx * pixel_size_x, topleft[1] + gy * pixel_size_y};
+        float g_out[3], final[3];
+        for (int c = 0; c < 3; ++c) {
+          g_out[c] = grad_out_rgb[3 * pix + c];
+          final[c] = out_rgb[3 * pix + c];
+        }
+        float out[3] = {0.0f, 0.0f, 0.0f};
+        float cum_alpha = 1.0f;
+        for (int i = 0; i < n_this; ++i) {
+          if (cum_alpha < thresh) break;
+          int32_t g = ids[i];
+          float alpha_ = fminf(alpha[g], 0.99f);
+          float G = gso_gaussian_2d_f64(mean + 2 * (int64_t)g, cov + 4 * (int64_t)g, pos);
+          if (alpha_ * G < GSO_MIN_RENDER_ALPHA) continue;
+          float coeff = alpha_ * cum_alpha * G;
+          double *a = acc + (size_t)g * row;
+          double partial_aG = 0.0;
+          for (int c = 0; c < 3; ++c) {
+            float col = color[3 * (int64_t)g + c];
+            out[c] += col * coeff;
+            gso_atomic_add(a + 7 + c, (double)(float)(coeff * g_out[c]));
+            partial_aG += (double)((col * cum_alpha - (final[c] - out[c]) / (1 - alpha_ * G)) * g_out[c]);
+          }
+          double gg[6];
+          gso_gaussian_2d_backward(mean + 2 * (int64_t)g, cov + 4 * (int64_t)g, pos,
+                                   (float)(partial_aG * alpha_ * G), gg);
+          for (int k = 0; k < 6; ++k) gso_atomic_add(a + k, gg[k]);
+          gso_atomic_add(a + 6, (double)(float)(partial_aG * G));
+          cum_alpha *= (1 - alpha_ * G);
+        }
+      }
+  }
+#pragma omp parallel for schedule(static)
+  for (int64_t g = 0; g < (int64_t)N; ++g) {
+    const double *a = acc + (size_t)g * row;
+    grad_mean[2 * g + 0] += (float)a[0];
+    grad_mean[2 * g + 1] += (float)a[1];
+    for (int k = 0; k < 4; ++k) grad_cov[4 * g + k] += (float)a[2 + k];
+    grad_alpha[g] += (float)a[6];
+    for (int k = 0; k < 3; ++k) grad_color[3 * g + k] += (float)a[7 + k];
+  }
+  free(acc);
+}

@@ -51,6 +51,14 @@ def lib():
         L.gso_tile_based_vol_rendering_backward_sh.argtypes = (
             [C.c_uint32] + [C.c_void_p] * 15 + [C.c_uint32] * 3 + [C.c_float] * 2 + [C.c_uint32] * 3
             + [C.c_float])
+        L.gso_gaussian_2d_f64.restype = C.c_float
+        L.gso_gaussian_2d_f64.argtypes = [C.c_void_p] * 3
+        L.gso_tile_based_vol_rendering_start_end.restype = None
+        L.gso_tile_based_vol_rendering_start_end.argtypes = (
+            [C.c_void_p] * 9 + [C.c_uint32] * 3 + [C.c_float] * 2 + [C.c_uint32] * 2 + [C.c_float, C.c_void_p])
+        L.gso_tile_based_vol_rendering_backward_start_end.restype = None
+        L.gso_tile_based_vol_rendering_backward_start_end.argtypes = (
+            [C.c_uint32] + [C.c_void_p] * 14 + [C.c_uint32] * 3 + [C.c_float] * 2 + [C.c_uint32] * 2 + [C.c_float])
         _lib = L
     return _lib
 
@@ -165,3 +173,47 @@ def render_sh_backward(mean, cov, sh_coeffs, alpha, start, end, gaussian_ids, ou
         int(n_tiles_h), int(n_tiles_w), float(pixel_size_x), float(pixel_size_y), int(H), int(W), int(C_),
         float(thresh))
     return g_mean, g_cov, g_sh, g_alpha
+
+
+# ---------------------------------------------------------------- legacy RGB path (8f rank 2)
+
+def gaussian_2d_f64(mean, cov, query):
+    mean, cov, query = _f32(mean), _f32(cov).reshape(-1), _f32(query)
+    return float(lib().gso_gaussian_2d_f64(_p(mean), _p(cov), _p(query)))
+
+
+def render_rgb_forward(mean, cov, color, alpha, start, end, gaussian_ids, topleft, tile_size, n_tiles_h,
+                       n_tiles_w, pixel_size_x, pixel_size_y, H, W, thresh, diagnostics=False):
+    """vol_render.h:716-798: RGB compositing over (start, end) ranges; -> out [H*W*3] (+ margin)."""
+    mean, cov, color, alpha = _f32(mean), _f32(cov).reshape(-1, 4), _f32(color), _f32(alpha)
+    start, end, ids = _i32(start), _i32(end), _i32(gaussian_ids)
+    if ids.size == 0:
+        ids = np.zeros(1, dtype=np.int32)
+    topleft = _f32(topleft)
+    out = np.zeros(H * W * 3, dtype=np.float32)
+    mg = np.ones(H * W, dtype=np.float32) if diagnostics else None
+    lib().gso_tile_based_vol_rendering_start_end(
+        _p(mean), _p(cov), _p(color), _p(alpha), _p(start), _p(end), _p(ids), _p(out), _p(topleft),
+        int(tile_size), int(n_tiles_h), int(n_tiles_w), float(pixel_size_x), float(pixel_size_y), int(H), int(W),
+        float(thresh), _p(mg))
+    return (out, mg) if diagnostics else out
+
+
+def render_rgb_backward(mean, cov, color, alpha, start, end, gaussian_ids, out, grad_out, topleft, tile_size,
+                        n_tiles_h, n_tiles_w, pixel_size_x, pixel_size_y, H, W, thresh):
+    """vol_render.h:800-923 -> (grad_mean [N,2], grad_cov [N,4], grad_color [N,3], grad_alpha [N])."""
+    mean, cov, color, alpha = _f32(mean), _f32(cov).reshape(-1, 4), _f32(color), _f32(alpha)
+    start, end, ids = _i32(start), _i32(end), _i32(gaussian_ids)
+    if ids.size == 0:
+        ids = np.zeros(1, dtype=np.int32)
+    out, grad_out, topleft = _f32(out).reshape(-1), _f32(grad_out).reshape(-1), _f32(topleft)
+    N = mean.shape[0]
+    g_mean = np.zeros((N, 2), dtype=np.float32)
+    g_cov = np.zeros((N, 4), dtype=np.float32)
+    g_color = np.zeros((N, 3), dtype=np.float32)
+    g_alpha = np.zeros(N, dtype=np.float32)
+    lib().gso_tile_based_vol_rendering_backward_start_end(
+        N, _p(mean), _p(cov), _p(color), _p(alpha), _p(start), _p(end), _p(ids), _p(out), _p(g_mean), _p(g_cov),
+        _p(g_color), _p(g_alpha), _p(grad_out), _p(topleft), int(tile_size), int(n_tiles_h), int(n_tiles_w),
+        float(pixel_size_x), float(pixel_size_y), int(H), int(W), float(thresh))
+    return g_mean, g_cov, g_color, g_alpha
