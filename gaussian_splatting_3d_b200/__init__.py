@@ -29,6 +29,7 @@ _ALIASES = {
     "utils.activations": "gaussian_splatting_3d_b200.utils.activations",
     "utils.schedulers": "gaussian_splatting_3d_b200.utils.schedulers",
     "utils.misc": "gaussian_splatting_3d_b200.utils.misc",
+    "utils.loss": "gaussian_splatting_3d_b200.utils.loss",
 }
 
 

@@ -10,7 +10,7 @@ from pathlib import Path
 PKG = Path(__file__).resolve().parent
 CSRC = PKG / "csrc"
 LIB = PKG / "libgs3d_b200.so"
-SOURCES = ["project.cu", "binning.cu", "composite.cu", "exchange.cu", "bands.cu", "train.cu"]
+SOURCES = ["project.cu", "binning.cu", "composite.cu", "exchange.cu", "bands.cu", "train.cu", "loss.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-O3", "-std=c++17", "-lineinfo",

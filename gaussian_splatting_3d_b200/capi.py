@@ -83,6 +83,8 @@ SIGNATURES = {
                                         _f, _i, _P]),
     "gs3d_composite_rgb_backward": (_i, [_u32, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _u32, _u32, _u32,
                                          _f, _f, _u32, _u32, _f, _i, _P]),
+    "gs3d_image_loss_scratch_bytes": (_sz, [_u32, _u32]),
+    "gs3d_image_loss": (_i, [_P, _P, _u32, _u32, _i, _f, _u32, _P, _P, _P, _sz, _P]),
     "gs3d_set_stage_counters": (_i, [_P]),
     "gs3d_adam_step": (_i, [_i, _ADAM, _d, _d, _d, _u32, _i, _P]),
     "gs3d_adc_classify": (_i, [_u32, _P, _P, _i, _f, _P, _i, _f, _P, _P]),

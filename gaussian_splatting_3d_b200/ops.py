@@ -424,6 +424,25 @@ def composite_rgb_backward(records, color, start, end, gaussian_ids, out, grad_o
         float(thresh), 1 if exact else 0, _stream(out)), "tile_based_vol_rendering_backward_start_end")
 
 
+# ---------------------------------------------------------------- loss step (8f rank 4)
+def image_loss(out, gt, base="l2", ssim_mult=0.0, window_size=11, want_grad=True):
+    """utils/loss.py:5-24 in one call: -> (loss [1] float32 on the device, d loss / d out [H,W,3] or None)."""
+    _chk(out, "out", _F32)
+    _chk(gt, "gt", _F32)
+    if out.dim() != 3 or out.size(2) != 3 or out.shape != gt.shape:
+        raise RuntimeError("image_loss: out and gt must both be [H, W, 3]")
+    code = {"l1": 1, "l2": 2}.get(base)
+    if code is None:
+        raise NotImplementedError(base)
+    H, W = out.size(0), out.size(1)
+    loss = torch.empty(1, dtype=_F32, device=out.device)
+    grad = torch.empty_like(out) if want_grad else None
+    scratch = _scratch(capi.lib.gs3d_image_loss_scratch_bytes(H, W), out.device)
+    check(capi.lib.gs3d_image_loss(ptr(out), ptr(gt), H, W, code, float(ssim_mult), int(window_size), ptr(loss),
+                                   ptr(grad), ptr(scratch), scratch.numel(), _stream(out)), "image_loss")
+    return loss, grad
+
+
 # ---------------------------------------------------------------- measurement aid
 def set_stage_counters(counters):
     """counters: int64 [2] CUDA tensor (zeroed) or None; see gs3d_set_stage_counters."""

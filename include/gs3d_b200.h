@@ -347,6 +347,18 @@ int gs3d_adc_apply(uint32_t N, const uint8_t *cls, int cls_is_keep_mask, const v
                    float scale_shrink_factor, const float *noise, float *mean_out, float *qvec_out,
                    float *svec_param_out, float *sh_coeffs_out, float *alpha_param_out, void *stream);
 
+/* ---- the loss step between the forward and the backward pass: utils/loss.py:5-24,
+ *   loss = ssim_mult * ssim_loss(out, gt, window_size, reduction="mean") + (1 - ssim_mult) * base(out, gt)
+ * base_loss 1 = F.l1_loss, 2 = F.mse_loss; ssim_loss is kornia's (un-vendored, unpinned -- requirements.txt:5;
+ * 0.6.x semantics: Gaussian window sigma 1.5, reflect border, C1 = 0.01^2, C2 = 0.03^2, eps 1e-12,
+ * clamp((1 - ssim)/2, 0, 1)).  out / gt are HWC float32 [H, W, 3].  Writes the scalar loss to *loss (device)
+ * and, when grad != NULL, d loss / d out to grad [H, W, 3].  window_size odd, <= 11; H, W > window_size/2.
+ * scratch >= gs3d_image_loss_scratch_bytes(H, W).  Deterministic (fixed-order reduction). */
+size_t gs3d_image_loss_scratch_bytes(uint32_t H, uint32_t W);
+int gs3d_image_loss(const float *out, const float *gt, uint32_t H, uint32_t W, int base_loss, float ssim_mult,
+                    uint32_t window_size, float *loss, float *grad, void *scratch, size_t scratch_bytes,
+                    void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -17,6 +17,10 @@ reference functions (imported from /root/reference by oracle/make_golden.py) tha
   reference_forward         gs/sh_renderer.py:188-316 (+ activations :318-324)
   split_gaussians / select_masked_gaussians / remove_low_alpha_mask   gs/sh_renderer.py:426-560,731-741
   adam_first_step           torch.optim.Adam as main_sh.py:193,238 uses it (re-created every step)
+  ssim / ssim_loss / get_loss_fn   utils/loss.py:5-24 over kornia 0.6.x `kornia.losses.ssim_loss` (kornia is
+                            un-vendored and unpinned, requirements.txt:5: PARITY UNPINNED at this boundary --
+                            no reference test or fixture holds an SSIM value; the published algorithm is
+                            restated and pinned by closed-form cases only, tests/test_loss.py)
 """
 import numpy as np
 import torch
@@ -276,3 +280,54 @@ def adam_first_step(params, grads, lrs, betas=(0.9, 0.99), eps=1e-8):
     opt = torch.optim.Adam([{"params": [p], "lr": lr} for p, lr in zip(ps, lrs)], lr=1e-3, betas=betas, eps=eps)
     opt.step()
     return [p.data for p in ps], opt
+
+
+# ---------------------------------------------------------------- loss (8f rank 4)
+
+def gaussian_window(window_size, sigma=1.5):
+    """kornia.filters.kernels.gaussian: exp(-x^2 / (2 sigma^2)) normalised (FP32)."""
+    x = torch.arange(window_size, dtype=torch.float32) - window_size // 2
+    if window_size % 2 == 0:
+        x = x + 0.5
+    g = torch.exp(-x.pow(2.0) / (2 * sigma ** 2))
+    return g / g.sum()
+
+
+def _filter2d_separable(img, k1d):
+    """kornia.filters.filter2d_separable(img, k, k, border_type="reflect") for img [B,C,H,W]."""
+    r = k1d.numel() // 2
+    c = img.shape[1]
+    x = F.pad(img, (r, r, r, r), mode="reflect")
+    x = F.conv2d(x, k1d.view(1, 1, 1, -1).expand(c, 1, 1, -1), groups=c)
+    return F.conv2d(x, k1d.view(1, 1, -1, 1).expand(c, 1, -1, 1), groups=c)
+
+
+def ssim(img1, img2, window_size, max_val=1.0, eps=1e-12):
+    """kornia.metrics.ssim (0.6.x, padding="same"): img [B,C,H,W] -> ssim map [B,C,H,W]."""
+    k = gaussian_window(window_size).to(img1)
+    C1, C2 = (0.01 * max_val) ** 2, (0.03 * max_val) ** 2
+    mu1, mu2 = _filter2d_separable(img1, k), _filter2d_separable(img2, k)
+    mu1_sq, mu2_sq, mu1_mu2 = mu1 ** 2, mu2 ** 2, mu1 * mu2
+    sigma1_sq = _filter2d_separable(img1 ** 2, k) - mu1_sq
+    sigma2_sq = _filter2d_separable(img2 ** 2, k) - mu2_sq
+    sigma12 = _filter2d_separable(img1 * img2, k) - mu1_mu2
+    num = (2.0 * mu1_mu2 + C1) * (2.0 * sigma12 + C2)
+    den = (mu1_sq + mu2_sq + C1) * (sigma1_sq + sigma2_sq + C2)
+    return num / (den + eps)
+
+
+def ssim_loss(img1, img2, window_size, max_val=1.0, eps=1e-12, reduction="mean"):
+    """kornia.losses.ssim_loss: clamp((1 - ssim) / 2, 0, 1), mean."""
+    loss = torch.clamp((1.0 - ssim(img1, img2, window_size, max_val, eps)) / 2, min=0, max=1)
+    return loss.mean() if reduction == "mean" else (loss.sum() if reduction == "sum" else loss)
+
+
+def get_loss_fn(loss_name, ssim_loss_mult, ssim_loss_win_size):
+    """utils/loss.py:5-24 op for op (out, gt are [H,W,3])."""
+    base = {"l2": F.mse_loss, "l1": F.l1_loss}[loss_name]
+
+    def loss_fn(out, gt):
+        return ssim_loss_mult * ssim_loss(out.moveaxis(-1, 0).unsqueeze(0), gt.moveaxis(-1, 0).unsqueeze(0),
+                                          ssim_loss_win_size, reduction="mean") + (1 - ssim_loss_mult) * base(out, gt)
+
+    return loss_fn

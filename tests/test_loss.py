@@ -1,0 +1,112 @@
+"""Loss step: utils/loss.py:5-24 = ssim_loss_mult * kornia ssim_loss + (1 - mult) * l1/l2.
+
+kornia is un-vendored and unpinned in the reference (requirements.txt:5), and no reference test holds an SSIM
+value: parity at this boundary is UNPINNED.  The oracle's restatement of the published algorithm
+(oracle/ref_torch.py) is checked here against closed-form cases and an independent direct (non-separable,
+explicit reflect indexing, FP64) evaluation; the kernels are then compared with the oracle: loss to 1e-6
+relative, gradient to 1e-5 of its max (FP32 summation order only)."""
+import numpy as np
+import pytest
+import torch
+
+DEV = "cuda:0"
+
+
+def _direct_ssim_map(x, y, win):
+    """Independent evaluation: explicit reflect indices, full 2-D window, float64."""
+    H, W = x.shape
+    r = win // 2
+    k = np.exp(-(np.arange(win) - r) ** 2 / (2 * 1.5 ** 2))
+    k /= k.sum()
+    k2 = np.outer(k, k)
+    refl = lambda j, n: (-j if j < 0 else (2 * (n - 1) - j if j >= n else j))  # noqa: E731
+    out = np.zeros((H, W))
+    for i in range(H):
+        for j in range(W):
+            ii = [refl(i + d, H) for d in range(-r, r + 1)]
+            jj = [refl(j + d, W) for d in range(-r, r + 1)]
+            px, py = x[np.ix_(ii, jj)], y[np.ix_(ii, jj)]
+            mu1, mu2 = (k2 * px).sum(), (k2 * py).sum()
+            s1, s2, s12 = (k2 * px * px).sum() - mu1 ** 2, (k2 * py * py).sum() - mu2 ** 2, (k2 * px * py).sum() - mu1 * mu2
+            out[i, j] = ((2 * mu1 * mu2 + 1e-4) * (2 * s12 + 9e-4)) / ((mu1 ** 2 + mu2 ** 2 + 1e-4) * (s1 + s2 + 9e-4) + 1e-12)
+    return out
+
+
+def test_oracle_ssim_closed_forms_and_direct_evaluation():
+    from oracle import ref_torch as R
+
+    g = torch.Generator().manual_seed(0)
+    x = torch.rand(1, 3, 20, 17, generator=g)
+    assert torch.allclose(R.ssim(x, x, 11), torch.ones_like(x), atol=1e-5)          # identical images
+    assert float(R.ssim_loss(x, x, 11)) < 1e-6
+    a, b = 0.3, 0.7                                                                 # constant images
+    want = (2 * a * b + 1e-4) / (a * a + b * b + 1e-4)
+    got = R.ssim(torch.full((1, 1, 16, 16), a), torch.full((1, 1, 16, 16), b), 11)
+    # FP32 cancellation in E[x^2] - mu^2 (~1e-8) against C2 = 9e-4: the second factor is 1 only to ~1e-4
+    assert torch.allclose(got, torch.full_like(got, want), atol=3e-4)
+    w = R.gaussian_window(11)
+    assert abs(float(w.sum()) - 1) < 1e-6 and float(w[5]) == float(w.max()) and torch.allclose(w, w.flip(0))
+    y = torch.rand(1, 3, 20, 17, generator=g)
+    m = R.ssim(x, y, 11)[0, 1].numpy()
+    d = _direct_ssim_map(x[0, 1].double().numpy(), y[0, 1].double().numpy(), 11)
+    assert np.abs(m - d).max() < 2e-5
+    lf = R.get_loss_fn("l2", 0.2, 11)
+    out, gt = x[0].moveaxis(0, -1).contiguous(), y[0].moveaxis(0, -1).contiguous()
+    want = 0.2 * np.clip((1 - np.stack([_direct_ssim_map(out[..., c].double().numpy(), gt[..., c].double().numpy(), 11)
+                                        for c in range(3)])) / 2, 0, 1).mean() + 0.8 * float(((out - gt) ** 2).mean())
+    assert abs(float(lf(out, gt)) - want) < 1e-6
+
+
+def test_loss_rejects_cpu_tensors_and_bad_windows():
+    from gaussian_splatting_3d_b200.utils.loss import image_loss
+
+    with pytest.raises(RuntimeError, match="CUDA"):
+        image_loss(torch.zeros(8, 8, 3), torch.zeros(8, 8, 3), "l2", 0.2, 11)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("H,W", [(256, 256), (53, 47), (840, 1297), (7, 6)])
+@pytest.mark.parametrize("base,mult,win", [("l2", 0.2, 11), ("l1", 0.5, 7), ("l2", 0.0, 11), ("l1", 1.0, 11)])
+def test_gpu_loss_and_gradient_match_oracle(H, W, base, mult, win):
+    from gaussian_splatting_3d_b200.utils.loss import image_loss
+    from oracle import ref_torch as R
+
+    if win // 2 >= min(H, W):
+        pytest.skip("reflect padding needs the window radius < image size")
+    g = torch.Generator().manual_seed(H * 1000 + W)
+    gt = torch.rand(H, W, 3, generator=g)
+    out = (gt + 0.25 * torch.randn(H, W, 3, generator=g)).clamp(-0.2, 1.3)
+    out[: H // 3] = gt[: H // 3]  # a region where out == gt (ssim = 1, |diff| = 0)
+    o_ref = out.clone().requires_grad_(True)
+    want = R.get_loss_fn(base, mult, win)(o_ref, gt)
+    want.backward()
+    o = out.to(DEV).requires_grad_(True)
+    got = image_loss(o, gt.to(DEV), base, mult, win)
+    (got * 3.0).backward()  # non-unit upstream gradient
+    assert abs(float(got) - float(want)) <= 1e-6 * max(1.0, abs(float(want))) + 2e-7   # loss: 1e-6 relative
+    gw = o_ref.grad
+    err = float((o.grad.cpu() / 3.0 - gw).abs().max())
+    assert err <= 1e-5 * float(gw.abs().max()) + 1e-12, (err, float(gw.abs().max()))   # gradient: 1e-5 of max
+    again = image_loss(o.detach().requires_grad_(True), gt.to(DEV), base, mult, win)
+    assert float(again) == float(got)                                                  # deterministic reduction
+
+
+@pytest.mark.gpu
+def test_gpu_training_step_with_the_reference_loss():
+    """renderer forward -> get_loss_fn(cfg) loss (0.2 SSIM + 0.8 L2, conf/fern_sh.yaml:34-37) -> backward."""
+    from gaussian_splatting_3d_b200 import synthetic as S
+    from gaussian_splatting_3d_b200.utils.loss import get_loss_fn
+    from oracle import ref_torch as R
+
+    cam = S.make_camera("cfg1")
+    sc = S.make_scene("cfg1", seed=5)
+    cfg = S.make_cfg(device=DEV, sh_order=sc["C"], loss_fn="l2", ssim_loss_mult=0.2, ssim_loss_win_size=11)
+    r = S.renderer_from_scene(sc, cfg)
+    r.train()
+    tgt = S.make_target(cam, 5).to(DEV)
+    out = r(sc["c2w"].to(DEV), cam)
+    loss = get_loss_fn(cfg)(out, tgt)
+    loss.backward()
+    want = R.get_loss_fn("l2", 0.2, 11)(out.detach().cpu(), tgt.cpu())
+    assert abs(float(loss) - float(want)) <= 1e-6
+    assert r.sh_coeffs.grad is not None and torch.isfinite(r.sh_coeffs.grad).all() and float(r.mean.grad.abs().max()) > 0
