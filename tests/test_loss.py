@@ -83,7 +83,7 @@ def test_gpu_loss_and_gradient_match_oracle(H, W, base, mult, win):
     o = out.to(DEV).requires_grad_(True)
     got = image_loss(o, gt.to(DEV), base, mult, win)
     (got * 3.0).backward()  # non-unit upstream gradient
-    assert abs(float(got) - float(want)) <= 1e-6 * max(1.0, abs(float(want))) + 2e-7   # loss: 1e-6 relative
+    assert abs(float(got.detach()) - float(want.detach())) <= 1e-6 * max(1.0, abs(float(want))) + 2e-7   # loss: 1e-6 relative
     gw = o_ref.grad
     err = float((o.grad.cpu() / 3.0 - gw).abs().max())
     assert err <= 1e-5 * float(gw.abs().max()) + 1e-12, (err, float(gw.abs().max()))   # gradient: 1e-5 of max

@@ -42,8 +42,40 @@ def timed(fn, k, world, dev):
     return ms
 
 
+def bench_loss():
+    """Loss step at cfg-2 resolution: fused kernels vs the same loss composed from torch ops on the GPU
+    (what kornia's ssim_loss + F.mse_loss launch), forward + backward to d loss / d out."""
+    from gaussian_splatting_3d_b200.utils.loss import image_loss
+    from oracle import ref_torch as R  # the torch-op composition, used here as the timed baseline
+
+    dev = torch.device("cuda:0")
+    cam = S.make_camera("cfg2")
+    g = torch.Generator().manual_seed(0)
+    gt = torch.rand(cam.h, cam.w, 3, generator=g).to(dev)
+    out = (gt + 0.1 * torch.randn(cam.h, cam.w, 3, generator=g).to(dev)).requires_grad_(True)
+    ref_fn = R.get_loss_fn("l2", 0.2, 11)
+
+    def ours():
+        out.grad = None
+        image_loss(out, gt, "l2", 0.2, 11).backward()
+
+    def torch_ops():
+        out.grad = None
+        ref_fn(out, gt).backward()
+
+    res = {}
+    for name, fn in (("fused", ours), ("torch_ops", torch_ops)):
+        for _ in range(3):
+            fn()
+        res[name] = timed(fn, 20, 1, dev)
+    print(json.dumps({"config": "loss", "image": [cam.w, cam.h], "metric": "loss fwd+bwd ms (0.2 SSIM(11) + 0.8 L2)",
+                      "ms": res, "speedup": res["torch_ops"] / res["fused"]}), flush=True)
+
+
 def main():
     which = sys.argv[1] if len(sys.argv) > 1 else "cfg3"
+    if which == "loss":
+        return bench_loss()
     steps = int(sys.argv[2]) if len(sys.argv) > 2 else 20
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
