@@ -34,10 +34,23 @@ radix_hist_kernel(const uint32_t *__restrict__ keys, uint32_t n, int shift, uint
   h[threadIdx.x] = 0;
   __syncthreads();
   size_t base = (size_t)blockIdx.x * SORT_TILE;
+  if (base + SORT_TILE <= n && (reinterpret_cast<uintptr_t>(keys) & 15) == 0) {
+    // full tile: 16-byte loads (a histogram does not care which thread counts which key)
+    const uint4 *k4 = reinterpret_cast<const uint4 *>(keys + base);
+#pragma unroll
+    for (int i = 0; i < SORT_IPT / 4; ++i) {
+      const uint4 v = k4[i * SORT_THREADS + threadIdx.x];
+      atomicAdd(&h[(v.x >> shift) & mask], 1u);
+      atomicAdd(&h[(v.y >> shift) & mask], 1u);
+      atomicAdd(&h[(v.z >> shift) & mask], 1u);
+      atomicAdd(&h[(v.w >> shift) & mask], 1u);
+    }
+  } else {
 #pragma unroll 4
-  for (int i = 0; i < SORT_IPT; ++i) {
-    size_t e = base + (size_t)i * SORT_THREADS + threadIdx.x;
-    if (e < n) atomicAdd(&h[(keys[e] >> shift) & mask], 1u);
+    for (int i = 0; i < SORT_IPT; ++i) {
+      size_t e = base + (size_t)i * SORT_THREADS + threadIdx.x;
+      if (e < n) atomicAdd(&h[(keys[e] >> shift) & mask], 1u);
+    }
   }
   __syncthreads();
   uint32_t c = h[threadIdx.x];
@@ -562,12 +575,29 @@ emit_kernel(uint32_t N, uint32_t n_dub, uint32_t n_tiles_w, const uint32_t *__re
 __global__ void __launch_bounds__(256)
 ranges_kernel(uint32_t n_dub, const uint32_t *__restrict__ tile_keys, int32_t *__restrict__ start,
               int32_t *__restrict__ end, uint32_t n_tiles) {
-  uint32_t g = blockIdx.x * 256 + threadIdx.x;
-  if (g >= n_dub) return;
-  uint32_t t = tile_keys[g];
-  if (t >= n_tiles) return;  // cannot happen for rects clamped to the image
-  if (g == 0 || tile_keys[g - 1] != t) start[t] = (int32_t)g;
-  if (g == n_dub - 1 || tile_keys[g + 1] != t) end[t] = (int32_t)(g + 1);
+  // four consecutive keys per thread (one 16-byte load) plus the two neighbours
+  const size_t g0 = 4 * ((size_t)blockIdx.x * 256 + threadIdx.x);
+  if (g0 >= n_dub) return;
+  uint32_t k[6];
+  const bool vec = g0 + 4 <= n_dub && (reinterpret_cast<uintptr_t>(tile_keys) & 15) == 0;
+  if (vec) {
+    const uint4 v = *reinterpret_cast<const uint4 *>(tile_keys + g0);
+    k[1] = v.x; k[2] = v.y; k[3] = v.z; k[4] = v.w;
+  } else {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) k[1 + i] = g0 + i < n_dub ? tile_keys[g0 + i] : 0xffffffffu;
+  }
+  k[0] = g0 > 0 ? tile_keys[g0 - 1] : 0xffffffffu;
+  k[5] = g0 + 4 < n_dub ? tile_keys[g0 + 4] : 0xffffffffu;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const size_t g = g0 + i;
+    if (g >= n_dub) break;
+    const uint32_t t = k[1 + i];
+    if (t >= n_tiles) continue;  // cannot happen for rects clamped to the image
+    if (g == 0 || k[i] != t) start[t] = (int32_t)g;
+    if (g == n_dub - 1 || k[2 + i] != t) end[t] = (int32_t)(g + 1);
+  }
 }
 
 __global__ void __launch_bounds__(256)
@@ -701,7 +731,7 @@ int gs3d_tile_culling_aabb_start_end(uint32_t N, uint32_t n_dub, uint32_t n_tile
   }
   // 4. tile ranges (+ optional reconstruction of the reference's sorted int64 keys)
   const uint32_t nbd = div_up(n_dub, 256u);
-  ranges_kernel<<<nbd, 256, 0, st>>>(n_dub, kcur, start, end, n_tiles);
+  ranges_kernel<<<div_up(n_dub, 1024u), 256, 0, st>>>(n_dub, kcur, start, end, n_tiles);
   GS3D_LAUNCH_CHECK();
   if (sorted_keys) {
     keys64_kernel<<<nbd, 256, 0, st>>>(n_dub, kcur, gaussian_ids, depth, sorted_keys);
