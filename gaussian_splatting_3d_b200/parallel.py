@@ -44,6 +44,8 @@ class FlatGradients:
     gs3d_rows_pull_marked): each GPU ingests ~(1 + 1/n) * U rows instead of n * U -- the form that
     scales to 8 ranks, where the push form is bound by the NVLink packet rate of 16-byte reductions.
 
+    sparse_reset=True (single GPU as well): zero() clears only the rows marked by the previous backward.
+
     sparse=True: the compositing backward marks the Gaussians whose gradient rows it writes; exchange()
     ORs the marks over the ranks (3 MB all-reduce), packs the union rows of all five blocks into one
     [U, 60] matrix (gs3d_rows_gather), all-reduces that -- U * 240 B instead of N * 236 B -- and
@@ -52,7 +54,8 @@ class FlatGradients:
 
     ORDER = ("sh_coeffs", "mean", "qvec", "svec_before_activation", "alpha_before_activation")
 
-    def __init__(self, module, fused=False, group=None, use_multicast=True, sparse=False, push=False, pull=False):
+    def __init__(self, module, fused=False, group=None, use_multicast=True, sparse=False, push=False, pull=False,
+                 sparse_reset=False):
         self.names = list(self.ORDER)
         self.params = [getattr(module, n) for n in self.names]
         total = sum(p.numel() for p in self.params)
@@ -64,7 +67,12 @@ class FlatGradients:
         self.push = (bool(push) or self.pull) and multi
         self.fused = bool(fused) and multi and not self.push
         self.sparse = bool(sparse) and not self.fused and not self.push
-        self.touched = torch.zeros(N, dtype=torch.uint8, device=dev) if (self.sparse or self.push) else None
+        # sparse_reset (any world size, no exchange implied): zero() clears only the rows the previous
+        # backward touched (marks from the compositing backward) instead of filling all 708 MB -- a view
+        # touches a few percent of the Gaussians
+        self.sparse_reset = bool(sparse_reset) and not self.fused and not self.push and dev.type == "cuda"
+        self.touched = (torch.zeros(N, dtype=torch.uint8, device=dev)
+                        if (self.sparse or self.push or self.sparse_reset) else None)
         self.last_union_rows = None
         self.handle = None
         self.local = self.local_views = self.union = self.union_handle = None
@@ -196,6 +204,10 @@ class FlatGradients:
                 resets()
             self._marks_ev = None
             self.flat, self.views, self.union = cur["flat"], cur["views"], cur["union"]
+        elif self.sparse_reset and self.module is not None:
+            from . import ops
+
+            ops.rows_zero_marked(self.touched, self.views, clear_marks=True)
         else:
             self.flat.zero_()
             if self.touched is not None:

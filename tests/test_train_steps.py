@@ -252,3 +252,36 @@ def test_gpu_training_loop_with_fused_adam_and_adc_runs_like_the_reference_loop(
         # so parameters agree wherever the gradient's sign is stable: compare in the bulk
         close = ((a - b).abs() <= 1e-4 * (1 + b.abs())).float().mean()
         assert float(close) > 0.99, (k, float(close))
+
+
+@pytest.mark.gpu
+def test_gpu_flat_gradients_sparse_reset_matches_plain_autograd():
+    """FlatGradients(sparse_reset=True): persistent flat buffer, reset clears only the rows the previous
+    backward marked.  Over several steps with different views the gradients must equal plain autograd's
+    (fresh zero-filled tensors) -- a stale row would show up as a difference on an untouched Gaussian."""
+    from gaussian_splatting_3d_b200 import parallel as P
+    from gaussian_splatting_3d_b200 import synthetic as S
+
+    cam = S.make_camera("cfg1")
+    sc = S.make_scene("cfg1", seed=7)
+    views = [sc["c2w"]] + S.ring_cameras(4, radius=7.0)[:3]
+    tgt = S.make_target(cam, 7).to(DEV)
+    a = S.renderer_from_scene(sc, S.make_cfg(device=DEV, sh_order=sc["C"]))
+    b = S.renderer_from_scene(sc, S.make_cfg(device=DEV, sh_order=sc["C"]))
+    a.train()
+    b.train()
+    flat = P.FlatGradients(a, sparse_reset=True).attach(a)
+    for v in views:
+        c2w = v.to(DEV)
+        flat.zero()
+        flat.backward_into(((a(c2w, cam) - tgt) ** 2).mean())
+        for p in b.parameters():
+            p.grad = None
+        ((b(c2w, cam) - tgt) ** 2).mean().backward()
+        for k in NAMES:
+            ga, gb = getattr(a, k).grad, getattr(b, k).grad
+            assert ga.data_ptr() == dict(zip(flat.names, flat.views))[k].data_ptr()  # .grad aliases the flat buffer
+            zero_b = gb.reshape(gb.shape[0], -1).abs().sum(dim=1) == 0
+            assert float(ga.reshape(ga.shape[0], -1)[zero_b].abs().max()) == 0.0, k      # no stale rows
+            # atomics order differs between the two runs: 1e-3 relative (gradient tolerance of the north star)
+            assert float((ga - gb).abs().max()) <= 1e-3 * float(gb.abs().max()) + 1e-12, k
