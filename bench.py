@@ -350,19 +350,23 @@ def run_ours(args, rank, local_rank, world):
     roofline = None
     if dom:
         ach = algo[dom] / (kernels_ms[dom] * 1e-3) / 1e9
-        traffic, traffic_src = None, None
+        traffic, traffic_src, issue = None, None, None
         tfile = ROOT / "profiles" / "ncu_traffic.json"
         if name == "cfg2" and args.n_gaussians is None and tfile.exists():
             try:  # dram__bytes_read.sum + dram__bytes_write.sum of one ncu --set full capture of this workload
                 t = json.loads(tfile.read_text()).get(dom)
                 if t:
                     traffic, traffic_src = t["traffic"], t["source"]
+                    # what actually bounds the compositing kernels (same capture): issue slots / pipes
+                    issue = {k: t[k] for k in ("issue_slot_pct", "fma_pipe_pct", "lsu_pipe_pct", "smem_wavefront_pct",
+                                               "warps_active_pct") if t.get(k) is not None}
             except Exception:
                 pass
         roofline = {"kernel": dom, "bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s",
                     "frac": ach / hbm_peak, "traffic": traffic, "traffic_source": traffic_src,
                     "peak_source": peak_src, "algorithmic_bytes": algo[dom], "launch_ms": kernels_ms[dom],
                     "staged_duplicates": {"fwd": staged_fwd, "bwd": staged_bwd, "n_dub": n_dub},
+                    "ncu_utilisation_pct_of_peak": issue,
                     "algorithmic_bytes_if_all_staged": upper.get(dom),
                     "note": "compositing is FP32-issue / shared-memory bound, not HBM bound (DESIGN.md: ncu "
                             "issue-slot utilisation 64-69 %, FMA pipe 42-47 %, DRAM < 2 %); algorithmic bytes "
