@@ -10,7 +10,7 @@ for arg in "$@"; do
   name="${arg%%:*}"; flags="${arg#*:}"
   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -lineinfo -Xcompiler -fPIC -shared -cudart shared \
     -DGS3D_ONLY_C4 $flags -o build/ablate/libgs3d_$name.so \
-    gaussian_splatting_3d_b200/csrc/project.cu gaussian_splatting_3d_b200/csrc/binning.cu gaussian_splatting_3d_b200/csrc/composite.cu gaussian_splatting_3d_b200/csrc/exchange.cu gaussian_splatting_3d_b200/csrc/bands.cu &
+    gaussian_splatting_3d_b200/csrc/project.cu gaussian_splatting_3d_b200/csrc/binning.cu gaussian_splatting_3d_b200/csrc/composite.cu gaussian_splatting_3d_b200/csrc/exchange.cu gaussian_splatting_3d_b200/csrc/bands.cu gaussian_splatting_3d_b200/csrc/train.cu gaussian_splatting_3d_b200/csrc/loss.cu &
 done
 wait
 ls build/ablate
