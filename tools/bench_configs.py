@@ -45,15 +45,32 @@ def timed(fn, k, world, dev):
 def bench_loss():
     """Loss step at cfg-2 resolution: fused kernels vs the same loss composed from torch ops on the GPU
     (what kornia's ssim_loss + F.mse_loss launch), forward + backward to d loss / d out."""
+    import torch.nn.functional as F
+
     from gaussian_splatting_3d_b200.utils.loss import image_loss
-    from oracle import ref_torch as R  # the torch-op composition, used here as the timed baseline
+
+    def torch_loss_fn(out, gt, mult=0.2, win=11):
+        """The same loss composed from torch ops, as kornia's ssim_loss + F.mse_loss launch it (baseline)."""
+        x, y = out.moveaxis(-1, 0).unsqueeze(0), gt.moveaxis(-1, 0).unsqueeze(0)
+        k = torch.exp(-(torch.arange(win, dtype=torch.float32, device=out.device) - win // 2).pow(2) / (2 * 1.5 ** 2))
+        k = k / k.sum()
+
+        def filt(img):
+            z = F.pad(img, (win // 2,) * 4, mode="reflect")
+            z = F.conv2d(z, k.view(1, 1, 1, -1).expand(3, 1, 1, -1), groups=3)
+            return F.conv2d(z, k.view(1, 1, -1, 1).expand(3, 1, -1, 1), groups=3)
+
+        mu1, mu2 = filt(x), filt(y)
+        s1, s2, s12 = filt(x * x) - mu1 ** 2, filt(y * y) - mu2 ** 2, filt(x * y) - mu1 * mu2
+        ssim = ((2 * mu1 * mu2 + 1e-4) * (2 * s12 + 9e-4)) / ((mu1 ** 2 + mu2 ** 2 + 1e-4) * (s1 + s2 + 9e-4) + 1e-12)
+        return mult * torch.clamp((1 - ssim) / 2, 0, 1).mean() + (1 - mult) * F.mse_loss(out, gt)
 
     dev = torch.device("cuda:0")
     cam = S.make_camera("cfg2")
     g = torch.Generator().manual_seed(0)
     gt = torch.rand(cam.h, cam.w, 3, generator=g).to(dev)
     out = (gt + 0.1 * torch.randn(cam.h, cam.w, 3, generator=g).to(dev)).requires_grad_(True)
-    ref_fn = R.get_loss_fn("l2", 0.2, 11)
+    ref_fn = torch_loss_fn
 
     def ours():
         out.grad = None
