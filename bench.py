@@ -219,14 +219,27 @@ def run_ours(args, rank, local_rank, world):
         flat = P.FlatGradients(r, fused=(mode == "fused"), sparse=(mode == "sparse"), push=(mode == "push"),
                                pull=(mode == "pull")).attach(r)
 
+    copy_stream = torch.cuda.Stream(device=dev)
+
     def step(e2e):
+        tgt_ready = None
         if e2e:
+            # the pose (48 B) is needed by the first kernel: current stream.  The 13 MB target image is not
+            # needed before the loss: its host->device copy runs on a copy stream beside the forward kernels
             c2w = c2w_host.to(dev, non_blocking=True)
-            tgt = tgt_host.to(dev, non_blocking=True)
+            main = torch.cuda.current_stream(dev)
+            copy_stream.wait_stream(main)  # (the previous step's consumers of the recycled block are done)
+            with torch.cuda.stream(copy_stream):
+                tgt = tgt_host.to(dev, non_blocking=True)
+                tgt_ready = torch.cuda.Event()
+                tgt_ready.record(copy_stream)
+            tgt.record_stream(main)
         else:
             c2w, tgt = c2w_dev, tgt_dev
         flat.zero()  # per-step reset of the gradient buffers (N > 1: side stream, overlaps the forward)
         out = r(c2w, cam)
+        if tgt_ready is not None:
+            torch.cuda.current_stream(dev).wait_event(tgt_ready)
         loss = ((out - tgt) ** 2).mean()
         flat.backward_into(loss)
         if world > 1:
