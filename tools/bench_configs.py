@@ -5,7 +5,7 @@ contract bench for cfg 2 / cfg 4):
   cfg3  500 k Gaussians, C=3, 1008x756: FULL training step = forward + L2 loss + backward +
         ADC position-grad accumulation (fused into the projection-backward kernel) + cnt + Adam.
   cfg4  cfg-2 scene, 8 cameras on a ring per step, views sharded over the ranks, gradients exchanged
-        (argv[3]: push | fused | sparse | allreduce); strong scaling: T_G for the same 8-camera step.
+        (argv[3]: pull | push | fused | sparse | allreduce); strong scaling: T_G for the same 8-camera step.
   cfg5  6 M Gaussians, C=4, 3840x2160 forward; on N ranks (torchrun) tile rows are sharded.
 
   python tools/bench_configs.py cfg3
@@ -141,11 +141,12 @@ def main():
                               "re-created every step like main_sh.py:238)",
                     "ms_per_step": ms, "value": 1000.0 / ms, "ms_per_step_by_optimiser": variants})
     elif which == "cfg4":
-        mode = sys.argv[3] if len(sys.argv) > 3 else "push"
+        mode = sys.argv[3] if len(sys.argv) > 3 else "pull"
         r.train()
         c2ws = [c.to(dev) for c in S.ring_cameras(8)]
         targets = [S.make_target(cam, i).to(dev) for i in range(8)]
-        flat = P.FlatGradients(r, fused=(mode == "fused"), sparse=(mode == "sparse"), push=(mode == "push")).attach(r)
+        flat = P.FlatGradients(r, fused=(mode == "fused"), sparse=(mode == "sparse"), push=(mode == "push"),
+                               pull=(mode == "pull"), sparse_reset=(world == 1)).attach(r)
 
         def step():
             P.view_sharded_step(r, flat, c2ws, cam, targets)

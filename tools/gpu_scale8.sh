@@ -7,5 +7,5 @@ for mode in push sparse allreduce fused; do
   echo "n8 $mode rc=$?"; tail -1 gpurun_out/bench_n8_$mode.json | cut -c1-200; grep -o '"kernels_ms.*"roofline' gpurun_out/bench_n8_$mode.json | cut -c1-400
 done
 timeout 300 $TR --nproc-per-node 4 --master-port 29522 bench.py --gpus 4 --steps 20 --warmup 3 > gpurun_out/bench_n4_push.json 2> gpurun_out/bench_n4_push.err; echo "n4 rc=$?"; tail -1 gpurun_out/bench_n4_push.json | cut -c1-200
-timeout 300 $TR --nproc-per-node 8 --master-port 29523 tools/bench_configs.py cfg4 10 push 2> gpurun_out/cfg4_n8.err | tee gpurun_out/cfg4_n8.json
+timeout 300 $TR --nproc-per-node 8 --master-port 29523 tools/bench_configs.py cfg4 10 pull 2> gpurun_out/cfg4_n8.err | tee gpurun_out/cfg4_n8.json
 timeout 300 $TR --nproc-per-node 8 --master-port 29524 tools/bench_configs.py cfg5 10 2> gpurun_out/cfg5_n8.err | tee gpurun_out/cfg5_n8.json
