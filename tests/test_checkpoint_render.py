@@ -56,3 +56,38 @@ def test_render_entry_matches_the_model_forward_and_writes_frames(tmp_path):
     assert np.array_equal(got, want.cpu().numpy())
     head = (tmp_path / "frames" / "frame_0000.ppm").read_bytes()[:15]
     assert head.startswith(f"P6\n{cam.w} {cam.h}\n255\n".encode())
+
+
+def test_render_entry_host_logic_on_cpu(tmp_path):
+    """No kernels: load_model restores a reference-style checkpoint (now_C from --sh-order or max_C), and
+    write_ppm clamps like the reference's save_img and writes a valid binary PPM."""
+    from gaussian_splatting_3d_b200 import render as RE
+
+    sc = S.make_scene("cfg1", seed=8, N=64)
+    cfg = S.make_cfg(device="cpu", sh_order=3)
+    state = {k: sc[k].clone() for k in KEYS - {"N", "cfg"}}
+    state["sh_coeffs"] = torch.zeros(64, 3, 9)
+    state.update(N=64, cfg=cfg)
+    torch.save(state, tmp_path / "m.pt")
+    m = RE.load_model(tmp_path / "m.pt", "cpu")
+    assert m.N == 64 and m.now_C == 3 and not m.training
+    assert RE.load_model(tmp_path / "m.pt", "cpu", sh_order=2).now_C == 2
+    img = torch.tensor([[[-0.5, 0.5, 2.0], [0.0, 1.0, 0.25]]])  # [1, 2, 3]
+    RE.write_ppm(tmp_path / "a.ppm", img)
+    raw = (tmp_path / "a.ppm").read_bytes()
+    assert raw.startswith(b"P6\n2 1\n255\n")
+    assert list(raw[-6:]) == [0, 128, 255, 0, 255, 64]
+
+
+def test_fused_adam_argument_validation():
+    from gaussian_splatting_3d_b200.optim import FusedAdam
+
+    w = torch.nn.Parameter(torch.zeros(3))
+    with pytest.raises(ValueError):
+        FusedAdam([w], lr=-1.0)
+    with pytest.raises(ValueError):
+        FusedAdam([w], betas=(1.0, 0.99))
+    opt = FusedAdam([{"params": [w], "lr": 0.5}], lr=1e-3, betas=(0.9, 0.99), single_step=True)
+    assert opt.param_groups[0]["lr"] == 0.5 and opt.param_groups[0]["betas"] == (0.9, 0.99)
+    assert opt.step() is None  # no gradients: nothing to launch, no CUDA needed
+    opt.zero_grad()
