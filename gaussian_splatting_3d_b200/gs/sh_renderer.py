@@ -124,6 +124,8 @@ class SHRenderer(torch.nn.Module):
             self.register_buffer("cnt", cnt)
         else:
             self.grad_mean, self.cnt = gm, cnt
+        # generation of the ADC buffers: parallel.sync_adc keeps a per-generation baseline
+        self._adc_epoch = getattr(self, "_adc_epoch", 0) + 1
 
     def set_cfg(self, cfg):
         g = cfg.get
@@ -277,6 +279,11 @@ class SHRenderer(torch.nn.Module):
         for name in _PARAM_NAMES:
             setattr(self, name, torch.nn.Parameter(new[name]))
         self.N = self.mean.shape[0]
+        # caller-owned gradient buffers (parallel.FlatGradients.attach) are views sized for the OLD
+        # parameters: drop them so the next backward cannot write past their end; the owner must
+        # build a new FlatGradients for the new tensors
+        if getattr(self, "grad_buffers", None) is not None:
+            self.grad_buffers = None
 
     def _param_data(self):
         return {name: getattr(self, name).data for name in _PARAM_NAMES}

@@ -228,6 +228,18 @@ def composite_sh_backward(records, sh, start, end, gaussian_ids, out, grad_out, 
         _chk(t, n, _F32)
     sg, sc = _sh_strides(sh, C_)
     gsg, gsc = _sh_strides(grad_sh, C_)
+    # the kernels index every per-Gaussian buffer with the ids of the tile lists (< M): a buffer sized
+    # for another M (e.g. gradient views kept across a split) would be written out of bounds
+    M = records.size(0)
+    for t, n, per in ((sh, "sh_coeffs", None), (grad_sh, "grad_sh_coeffs", None), (grad_mean, "grad_mean", 2),
+                      (grad_cov, "grad_cov", 4), (grad_alpha, "grad_alpha", 1), (touched, "touched", 1)):
+        if t is None:
+            continue
+        rows = t.size(0) if per is None else t.numel() // per
+        if rows != M or (per is not None and t.numel() != per * M):
+            raise RuntimeError(f"{n} holds {rows} rows but the staging records hold {M} Gaussians")
+    if out.numel() < H * W * 3 or grad_out.numel() < H * W * 3:
+        raise RuntimeError("out / grad_out must have H*W*3 elements")
     n_peers = 0 if not peer_ptrs else len(peer_ptrs)
     arr = (C.c_uint64 * max(n_peers, 1))(*([int(x) for x in peer_ptrs] if n_peers else [0]))
     check(capi.lib.gs3d_composite_sh_backward_peers(
@@ -256,8 +268,15 @@ def project_backward_fused(mask, mean, qvec, svec_param, alpha_param, svec_act, 
         accumulate = False
     else:
         gm, gq, gs, ga = out
-        for t, n in ((gm, "grad_mean"), (gq, "grad_qvec"), (gs, "grad_svec"), (ga, "grad_alpha")):
+        for t, n, per in ((gm, "grad_mean", 3), (gq, "grad_qvec", 4), (gs, "grad_svec", 3), (ga, "grad_alpha", 1)):
             _chk(t, n, _F32)
+            if t.numel() != per * N:
+                raise RuntimeError(f"{n} has {t.numel()} elements, expected {per} x N = {per * N}")
+    for t, n, per in ((mask, "mask", 1), (qvec, "qvec", 4), (svec_param, "svec", 3), (alpha_param, "alpha", 1),
+                      (g_mean2d, "grad_mean2d", 2), (g_cov, "grad_cov", 4), (g_alpha, "grad_alpha2d", 1),
+                      (grad_mean_acc, "grad_mean_acc", 1)):
+        if t is not None and t.numel() != per * N:
+            raise RuntimeError(f"{n} has {t.numel()} elements, expected {per} x N = {per * N}")
     check(capi.lib.gs3d_project_backward_fused(
         N, ptr(mask), ptr(mean), ptr(qvec), ptr(svec_param), ptr(alpha_param), int(svec_act),
         int(alpha_act), ptr(c2w), 1 if detach_depth else 0, ptr(g_mean2d), ptr(g_cov), ptr(g_alpha),
@@ -547,3 +566,41 @@ def adc_apply(plan, mean, qvec, svec_param, sh_coeffs, alpha_param, svec_act=1, 
                                   ptr(noise) if noise is not None else None, ptr(out[0]), ptr(out[1]), ptr(out[2]),
                                   ptr(out[3]), ptr(out[4]), _stream(mean)), "adc_apply")
     return out
+
+
+# ---------------------------------------------------------------- device guard
+# The kernels are launched on the CUDA *current* device with the stream of the tensors' device.  A model
+# that lives on another device than the current one (cfg.device = "cuda:1" without torch.cuda.set_device)
+# would launch on the wrong GPU: run such calls under that device's context (the reference has no guard
+# either -- render.cu:12 includes CUDAGuard.h and never uses it -- but there the mistake is silent).
+def _first_cuda_tensor(args, kwargs):
+    for a in list(args) + list(kwargs.values()):
+        if isinstance(a, torch.Tensor):
+            if a.is_cuda:
+                return a
+        elif isinstance(a, (list, tuple)):
+            for b in a:
+                if isinstance(b, torch.Tensor) and b.is_cuda:
+                    return b
+    return None
+
+
+def _device_guarded(fn):
+    import functools
+
+    @functools.wraps(fn)
+    def wrapped(*args, **kwargs):
+        t = _first_cuda_tensor(args, kwargs)
+        if t is not None and t.device.index != torch.cuda.current_device():
+            with torch.cuda.device(t.device):
+                return fn(*args, **kwargs)
+        return fn(*args, **kwargs)
+
+    return wrapped
+
+
+for _name, _fn in list(globals().items()):
+    if callable(_fn) and getattr(_fn, "__module__", None) == __name__ and not _name.startswith("_") \
+            and _name not in ("check", "ptr"):
+        globals()[_name] = _device_guarded(_fn)
+del _name, _fn

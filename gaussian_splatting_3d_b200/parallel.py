@@ -179,6 +179,15 @@ class FlatGradients:
             self.module.grad_buffers = None
             self.module = None
 
+    def _check_attached(self):
+        """The renderer drops `grad_buffers` when it replaces its parameters (split / prune / load):
+        this object then still aliases the OLD tensors and must be rebuilt."""
+        m = self.module
+        if m is not None and (m.grad_buffers is None or any(getattr(m, n) is not p
+                                                             for n, p in zip(self.names, self.params))):
+            raise RuntimeError("FlatGradients: the renderer's parameters were replaced (adaptive density control "
+                               "or load) after attach(); build a new FlatGradients(renderer).attach(renderer)")
+
     def _barrier(self):
         if self.handle is not None:
             self.handle.barrier(channel=0)
@@ -186,6 +195,7 @@ class FlatGradients:
             dist.barrier(group=self.group)
 
     def zero(self):
+        self._check_attached()
         if self.push and self.module is not None:
             from . import ops
 
@@ -219,6 +229,7 @@ class FlatGradients:
 
     def backward_into(self, loss):
         """Run backward for `loss`; the kernels add the leaf gradients into the flat buffer."""
+        self._check_attached()
         if self._aux_ev is not None:  # the private buffer must be clean before the backward adds into it
             torch.cuda.current_stream(self.flat.device).wait_event(self._aux_ev)
             self._aux_ev = None
@@ -318,24 +329,38 @@ def view_sharded_step(renderer, flat, c2ws, camera_info, targets, loss_fn=None, 
 def sync_adc(renderer, group=None):
     """Make the ADC statistics identical on all ranks (sh_renderer.py:602-623 semantics over the
     union of the step's views): cnt is summed; grad_mean is summed ('mean') or max-reduced ('max').
-    Each rank contributes only what it accumulated since the last sync."""
+    Each rank contributes only what it accumulated since the last sync.
+
+    The baseline of the last sync is dropped whenever the renderer replaces its ADC buffers
+    (adaptive_control -> _reset_adc_buffers after a split / prune / alpha reset): a baseline that
+    does not belong to the current buffers -- other shape, or the buffers were re-zeroed -- restarts
+    from zero.  With split_type 'mean_grad' and reduction 'mean' the statistic is ||mean.grad|| of the
+    ALREADY exchanged gradient, identical on every rank, so it is not summed again (that would inflate
+    it by the world size); only the fused / 2-D statistic is rank-local."""
     if not (dist.is_initialized() and dist.get_world_size(group) > 1):
         return
-    if not hasattr(renderer, "_adc_synced"):
-        renderer._adc_synced = (torch.zeros_like(renderer.grad_mean), torch.zeros_like(renderer.cnt))
-    gm0, cnt0 = renderer._adc_synced
+    base = getattr(renderer, "_adc_synced", None)
+    epoch = getattr(renderer, "_adc_epoch", 0)
+    if (base is None or base[2] != epoch or base[0].shape != renderer.grad_mean.shape
+            or base[1].shape != renderer.cnt.shape):
+        base = (torch.zeros_like(renderer.grad_mean), torch.zeros_like(renderer.cnt), epoch)
+    gm0, cnt0, _ = base
     d_cnt = renderer.cnt - cnt0
     dist.all_reduce(d_cnt, op=dist.ReduceOp.SUM, group=group)
     renderer.cnt = cnt0 + d_cnt
+    rank_local = getattr(renderer, "split_type", "2d_mean_grad") != "mean_grad"
     if renderer.split_reduction == "max":
         gm = renderer.grad_mean.clone()
-        dist.all_reduce(gm, op=dist.ReduceOp.MAX, group=group)
-    else:
+        if rank_local:
+            dist.all_reduce(gm, op=dist.ReduceOp.MAX, group=group)
+    elif rank_local:
         d_gm = renderer.grad_mean - gm0
         dist.all_reduce(d_gm, op=dist.ReduceOp.SUM, group=group)
         gm = gm0 + d_gm
+    else:
+        gm = renderer.grad_mean.clone()
     renderer.grad_mean = gm
-    renderer._adc_synced = (gm.clone(), renderer.cnt.clone())
+    renderer._adc_synced = (gm.clone(), renderer.cnt.clone(), epoch)
 
 
 # ---------------------------------------------------------------- tile-sharded rendering

@@ -95,6 +95,36 @@ def build(verbose=False, force=False):
     return dst
 
 
+REF_ROOT = Path("/root/reference")
+PY_OUT = OUT / "py"
+
+
+def stage_python(force=False):
+    """Stage the reference's UNMODIFIED Python packages (gs/*.py, utils/**/*.py) into the git-ignored
+    ``oracle/_ref/py`` so that tests on the GPU box can run the reference's own SHRenderer.forward /
+    backward and its training loop over this repo's ``_gs`` shim (INTEGRATION.md route 2).  Byte-for-byte
+    copies, never committed (``oracle/_ref/`` is in .gitignore), test infrastructure only."""
+    if not REF_ROOT.exists():
+        return PY_OUT if PY_OUT.exists() else None
+    marker = PY_OUT / ".staged"
+    if marker.exists() and not force:
+        return PY_OUT
+    if PY_OUT.exists():
+        shutil.rmtree(PY_OUT)
+    for pkg in ("gs", "utils"):
+        src_dir = REF_ROOT / pkg
+        for src in src_dir.rglob("*.py"):
+            rel = src.relative_to(REF_ROOT)
+            if rel.parts[:2] == ("gs", "src"):
+                continue
+            dst = PY_OUT / rel
+            dst.parent.mkdir(parents=True, exist_ok=True)
+            shutil.copy2(src, dst)
+    marker.write_text("staged from /root/reference (unmodified)\n")
+    return PY_OUT
+
+
 if __name__ == "__main__":
     p = build(verbose="-v" in sys.argv, force="-f" in sys.argv)
     print("reference extension:", p)
+    print("reference python:", stage_python(force="-f" in sys.argv))

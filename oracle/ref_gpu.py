@@ -26,7 +26,10 @@ def load_reference_extension():
     return mod
 
 
-def make_render_fn(ext):
+def make_render_fn(ext, bg_rgb=None):
+    """bg_rgb: None -> _render_sh (gs/renderer.py:672-828); a float32 [3] device tensor -> _render_sh_bg
+    (gs/renderer.py:831-993, the *_with_bg bindings)."""
+
     class _render_sh(torch.autograd.Function):
         """gs/renderer.py:672-828 (argument order, zero-initialised outputs, saved tensors)."""
 
@@ -34,8 +37,12 @@ def make_render_fn(ext):
         def forward(ctx, mean, cov, sh_coeffs, alpha, start, end, gaussian_ids, topleft, c2w, consts):
             H, W = consts[5], consts[6]
             out = torch.zeros([H * W * 3], dtype=torch.float32, device=mean.device)
-            ext.tile_based_vol_rendering_sh(mean, cov, sh_coeffs, alpha, start, end, gaussian_ids, out, topleft,
-                                            c2w, *consts)
+            if bg_rgb is None:
+                ext.tile_based_vol_rendering_sh(mean, cov, sh_coeffs, alpha, start, end, gaussian_ids, out,
+                                                topleft, c2w, *consts)
+            else:
+                ext.tile_based_vol_rendering_sh_with_bg(mean, cov, sh_coeffs, alpha, start, end, gaussian_ids, out,
+                                                        topleft, c2w, *consts, bg_rgb)
             ctx.save_for_backward(mean, cov, sh_coeffs, alpha, start, end, gaussian_ids, out, topleft, c2w)
             ctx.consts = consts
             return out
@@ -47,9 +54,14 @@ def make_render_fn(ext):
             grad_cov = torch.zeros_like(cov)
             grad_sh = torch.zeros_like(sh_coeffs)
             grad_alpha = torch.zeros_like(alpha)
-            ext.tile_based_vol_rendering_backward_sh(mean, cov, sh_coeffs, alpha, start, end, gaussian_ids, out,
-                                                     grad_mean, grad_cov, grad_sh, grad_alpha, grad.contiguous(),
-                                                     topleft, c2w, *ctx.consts)
+            if bg_rgb is None:
+                ext.tile_based_vol_rendering_backward_sh(mean, cov, sh_coeffs, alpha, start, end, gaussian_ids, out,
+                                                         grad_mean, grad_cov, grad_sh, grad_alpha,
+                                                         grad.contiguous(), topleft, c2w, *ctx.consts)
+            else:
+                ext.tile_based_vol_rendering_backward_sh_with_bg(
+                    mean, cov, sh_coeffs, alpha, start, end, gaussian_ids, out, grad_mean, grad_cov, grad_sh,
+                    grad_alpha, grad.contiguous(), topleft, c2w, *ctx.consts, bg_rgb)
             return grad_mean, grad_cov, grad_sh, grad_alpha, None, None, None, None, None, None
 
     return _render_sh.apply
@@ -58,9 +70,11 @@ def make_render_fn(ext):
 class ReferenceGPURenderer:
     """Holds leaf parameters on the GPU and renders like the reference's SHRenderer."""
 
-    def __init__(self, ext, scene, device, C, tile_size=16, frustum_radius=1.0, tile_D=6.0, T_thresh=1e-4):
+    def __init__(self, ext, scene, device, C, tile_size=16, frustum_radius=1.0, tile_D=6.0, T_thresh=1e-4,
+                 bg_rgb=None):
         self.ext = ext
-        self.render = make_render_fn(ext)
+        self.render = make_render_fn(ext, bg_rgb)
+        self.aux = None  # intermediate tensors of the last forward (for stage-by-stage comparison)
         self.dev = device
         self.C = C
         self.tile_size, self.frustum_radius, self.tile_D, self.T_thresh = tile_size, frustum_radius, tile_D, T_thresh
@@ -89,6 +103,8 @@ class ReferenceGPURenderer:
         sh = p["sh_coeffs"][mask].contiguous()
         alpha = alpha_act[mask].contiguous()
         mean2d, cov, JW, depth = R.project_gaussians(mean, qvec, svec_m, c2w, True)
+        if mean2d.requires_grad:
+            mean2d.retain_grad()  # sh_renderer.py:217-221
         n_dub, tl, br = R.tile_culling_aabb_count(mean2d, cov, tile, cam, self.tile_D)
         self.total_dub_gaussians = n_dub
         H, W = cam.h, cam.w
@@ -101,4 +117,6 @@ class ReferenceGPURenderer:
         ext.tile_culling_aabb_start_end(tl, br, ids, start, end, depth, nth, ntw)
         consts = (tile, nth, ntw, 1.0 / cam.fx, 1.0 / cam.fy, H, W, C, self.T_thresh)
         out = self.render(mean2d, cov, sh[..., : C * C].contiguous(), alpha, start, end, ids, topleft, c2w, consts)
+        self.aux = dict(mask=mask, mean2d=mean2d, cov=cov, depth=depth, tl=tl, br=br, n_dub=n_dub, ids=ids,
+                        start=start, end=end)
         return out.view(H, W, 3)
