@@ -252,30 +252,30 @@ __device__ __forceinline__ bool pair_decide(float px, float py, float dead, floa
 }
 
 // Stage `nb` Gaussians (ids already in s_ids) into shared memory with cp.async.
-template <int CC, int B>
+template <int CC, int B, int NT = NTHREADS>
 __device__ __forceinline__ void stage_batch(const CompositeParams &p, const int *s_ids, int nb,
                                             float4 *s_rec, float *s_sh) {
   constexpr int SHF = 3 * CC;
-  for (int e = threadIdx.x; e < nb * 3; e += NTHREADS) {
+  for (int e = threadIdx.x; e < nb * 3; e += NT) {
     int j = e / 3, r = e - 3 * j;
     cp_async_16(s_rec + e, p.records + 3 * (size_t)s_ids[j] + r);
   }
   // the compositing loops are unrolled by up to 4: pad with null records (threshold +inf: never
   // contributes) so they need no remainder handling
-  if (threadIdx.x >= NTHREADS - 9) {
-    const int e = nb * 3 + (NTHREADS - 1 - threadIdx.x);
+  if (threadIdx.x >= NT - 9) {
+    const int e = nb * 3 + (NT - 1 - threadIdx.x);
     if (e < ((nb + 3) & ~3) * 3)
       s_rec[e] = (e % 3 == 0) ? make_float4(0.f, 0.f, 0.f, __int_as_float(0x7f800000)) : make_float4(0.f, 0.f, 0.f, 0.f);
   }
   if (p.sh_vec) {
     constexpr int V = SHF / 4 > 0 ? SHF / 4 : 1;
-    for (int e = threadIdx.x; e < nb * V; e += NTHREADS) {
+    for (int e = threadIdx.x; e < nb * V; e += NT) {
       int j = e / V, r = (e - V * j) * 4;
       int c = r / CC, k = r - c * CC;
       cp_async_16(s_sh + j * SHF + r, p.sh + (size_t)s_ids[j] * p.sh_sg + c * p.sh_sc + k);
     }
   } else {
-    for (int e = threadIdx.x; e < nb * SHF; e += NTHREADS) {
+    for (int e = threadIdx.x; e < nb * SHF; e += NT) {
       int j = e / SHF, r = e - SHF * j;
       int c = r / CC, k = r - c * CC;
       cp_async_4(s_sh + e, p.sh + (size_t)s_ids[j] * p.sh_sg + c * p.sh_sc + k);
@@ -776,6 +776,343 @@ composite_bwd_kernel(const CompositeParams p) {
 }
 
 
+// ---------------------------------------------------------------- backward, second generation
+//
+// Same arithmetic as composite_bwd_kernel, restructured after its ncu profile (profiles/r1_ncu_composite_v4):
+//  * warp-uniform control flow.  A warp executes the contributing path whenever ANY lane contributes, so the
+//    per-lane branches of the first version bought nothing and cost BSSY/BSYNC pairs plus branch-resolve stalls.
+//    Here every decision is a vote: lanes that do not contribute run the same straight-line code with G = 0
+//    (coeff, alpha*G and every partial gradient are then exactly 0, T is multiplied by exactly 1).
+//  * the warp-private accumulator row of a (warp, Gaussian) pair is written exactly once per batch: plain
+//    stores instead of read-modify-write (rows of pairs that did not contribute stay zero from the last flush).
+//  * NW warps per CTA (8 = a 16x16 tile, 4 = a 16x8 half tile: the batch barrier then waits for the slowest of
+//    4 warps instead of 8 and twice as many independent CTAs share an SM).
+//  * DIRECT: no CTA-level accumulators at all -- each warp reduces its own 3*C*C + 6 sums into global memory
+//    (red.global.add.v4.f32 from 14 lanes), which frees 57 KB of shared memory per CTA, allows batches of 64
+//    (one barrier per 64 Gaussians) and removes the flush pass, at 8x the global reductions.
+
+// One float4 (quad q of a Gaussian's [3*CC + 6]-float gradient row, padded to a multiple of 4) -> global memory.
+template <int CC>
+__device__ __forceinline__ void emit_quad(const CompositeParams &p, size_t g, int q, float4 s) {
+  constexpr int SHF = 3 * CC;
+  const float sv4[4] = {s.x, s.y, s.z, s.w};
+  const int r0 = 4 * q;
+  if (CC % 4 == 0 && p.gsh_vec && r0 + 3 < SHF) {
+    const int c = r0 / CC, k = r0 - c * CC;
+    const size_t off = g * p.gsh_sg + c * p.gsh_sc + k;
+    if (p.g_sh_mc) {
+      multimem_red_add_v4(p.g_sh_mc + off, s);  // one instruction, the switch adds it on every GPU
+    } else if (p.n_peers > 0) {
+      for (int r = 0; r < p.n_peers; ++r) red_add_v4(p.g_sh_peer[r] + off, s);
+    } else {
+      red_add_v4(p.g_sh + off, s);
+    }
+    return;
+  }
+#pragma unroll
+  for (int u = 0; u < 4; ++u) {
+    const int r = r0 + u;
+    const float val = sv4[u];
+    if (val == 0.f) continue;
+    if (r < SHF) {
+      const int c = r / CC, k = r - c * CC;
+      const size_t off = g * p.gsh_sg + c * p.gsh_sc + k;
+      if (p.n_peers > 0) {
+        for (int q2 = 0; q2 < p.n_peers; ++q2) atomicAdd(p.g_sh_peer[q2] + off, val);
+      } else {
+        atomicAdd(p.g_sh + off, val);
+      }
+    } else {
+      const int v = r - SHF;
+      if (v == 0) atomicAdd(p.g_mean + 2 * g, val);
+      else if (v == 1) atomicAdd(p.g_mean + 2 * g + 1, val);
+      else if (v == 2) atomicAdd(p.g_cov + 4 * g, val);
+      else if (v == 3) { atomicAdd(p.g_cov + 4 * g + 1, val); atomicAdd(p.g_cov + 4 * g + 2, val); }
+      else if (v == 4) atomicAdd(p.g_cov + 4 * g + 3, val);
+      else if (v == 5) atomicAdd(p.g_alpha + g, val);
+    }
+  }
+}
+
+// Sum the NW warp-private accumulator rows of one batch, reduce into global memory, re-zero.
+template <int CC, int B, int NW>
+__device__ __forceinline__ void flush_batch2(const CompositeParams &p, float *s_acc, const int *s_ids_b, int nb) {
+  constexpr int ROWP = (3 * CC + 6 + 3) & ~3;
+  constexpr int NQ = ROWP / 4;
+  for (int e = threadIdx.x; e < nb * NQ; e += NW * 32) {
+    const int j = e / NQ, q = e - NQ * j;
+    float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int w = 0; w < NW; ++w) {
+      float4 *a4 = reinterpret_cast<float4 *>(s_acc + (w * B + j) * ROWP) + q;
+      float4 v = *a4;
+      s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+      *a4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    if (s.x == 0.f && s.y == 0.f && s.z == 0.f && s.w == 0.f) continue;
+    const size_t g = (size_t)s_ids_b[j];
+    if (p.touched) p.touched[g] = 1;
+    emit_quad<CC>(p, g, q, s);
+  }
+}
+
+template <int C, int B, bool EXACT, bool RGB, int NW, bool DIRECT>
+__global__ void __launch_bounds__(NW * 32, (NW == 8 ? 3 : 6))
+composite_bwd2_kernel(const CompositeParams p) {
+  constexpr int CC = C * C;
+  constexpr int SHF = 3 * CC;
+  constexpr int ROW = SHF + 6;            // 3*CC SH sums, then gmx gmy g00 g01 g11 galpha
+  constexpr int ROWP = (ROW + 3) & ~3;    // padded to float4
+  constexpr int NQ = ROWP / 4;
+  constexpr int KL = CC < 16 ? CC : 16;   // lanes per half that own an SH column
+  constexpr int NT = NW * 32;
+  constexpr int SUBS = 8 / NW;            // CTAs per 16x16 tile
+  constexpr int ACC = NW * B * ROWP;      // floats per accumulator buffer (!DIRECT)
+  constexpr uint32_t FULL = 0xffffffffu;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  float4 *s_rec = reinterpret_cast<float4 *>(smem_raw);           // [2][B][3]
+  float *s_sh = reinterpret_cast<float *>(s_rec + 2 * B * 3);     // [2][B][SHF]
+  float *s_w = s_sh + 2 * B * SHF;                                // [NW][9][WROW]
+  float *s_acc = s_w + NW * 9 * WROW;                             // DIRECT ? [NW][ROWP] : [2][NW][B][ROWP]
+  int *s_ids = reinterpret_cast<int *>(s_acc + (DIRECT ? NW * ROWP : 2 * ACC));  // [4][B] ring
+
+  const int tile_id = blockIdx.x / SUBS, sub = blockIdx.x - tile_id * SUBS;
+  const int tile_y = tile_id / p.ntw, tile_x = tile_id - tile_y * p.ntw;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int lx = 8 * (warp & 1) + (lane & 7), ly = 4 * (warp >> 1) + (lane >> 3) + sub * (2 * NW);
+  const uint32_t gx = tile_x * TILE + lx, gy = tile_y * TILE + ly;
+  const bool inside = gx < p.W && gy < p.H;
+  const size_t pix = (size_t)gy * p.W + gx;
+
+  const int first = p.start[tile_id];
+  if (first == -1) return;
+  const int n_this = p.end[tile_id] - first;
+  if (n_this <= 0) return;
+
+  const float px = p.topleft[0] + gx * p.psx, py = p.topleft[1] + gy * p.psy;
+  Basis<CC> Y;
+  // Yt = Y_k(pixel 16*half + i), i = 0..15, for this lane's (k = lane & 15, half = lane >> 4): transposed
+  // through the warp's (not yet used) exchange tile, eight basis functions per round, kept as packed pairs.
+  const int kcol = lane & 15, half = lane >> 4;
+  f32x2 Yt[8];
+  {
+    float Yf[CC];
+    if constexpr (RGB) Yf[0] = 1.0f;  // colour gradient = plain sum of the per-pixel weights
+    else pixel_basis<C>(p.c2w, px, py, Yf);
+    Y.set(Yf);
+    float *tr = s_w + warp * 9 * WROW;  // [32][9] floats (288 <= 9 * WROW)
+#pragma unroll
+    for (int i = 0; i < 8; ++i) Yt[i] = 0ull;
+#pragma unroll
+    for (int rd = 0; rd < (CC + 7) / 8; ++rd) {
+#pragma unroll
+      for (int k = 0; k < 8; ++k)
+        if (8 * rd + k < CC) tr[lane * 9 + k] = inside ? Yf[8 * rd + k] : 0.0f;
+      __syncwarp();
+      if ((kcol >> 3) == rd && kcol < CC) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+          Yt[i] = pack2(tr[(16 * half + 2 * i) * 9 + (kcol & 7)], tr[(16 * half + 2 * i + 1) * 9 + (kcol & 7)]);
+      }
+      __syncwarp();
+    }
+  }
+  if constexpr (!DIRECT) {
+    for (int e = threadIdx.x; e < 2 * ACC; e += NT) s_acc[e] = 0.0f;
+  }
+
+  // f* = colour still to come after the current Gaussian (the reference's `final - prefix`,
+  // vol_render_sh.h:336-342), kept as a running remainder instead of final and prefix separately
+  float g0 = 0.f, g1 = 0.f, g2 = 0.f, f0 = 0.f, f1 = 0.f, f2 = 0.f;
+  if (inside) {
+    g0 = p.grad_out[3 * pix + 0]; g1 = p.grad_out[3 * pix + 1]; g2 = p.grad_out[3 * pix + 2];
+    f0 = p.out_saved[3 * pix + 0]; f1 = p.out_saved[3 * pix + 1]; f2 = p.out_saved[3 * pix + 2];
+  }
+  float T = 1.0f;
+  const float thresh = p.thresh;
+  float dead = (inside && !(1.0f < thresh)) ? 0.0f : DEAD;
+  const int32_t *ids = p.ids + first;
+  const int n_batches = (n_this + B - 1) / B;
+  constexpr float INV_K = 1.0f / (-0.5f * 1.4426950408889634f);  // undo the conic pre-scale
+  const bool id_lane = threadIdx.x < B;
+  static_assert(B <= NW * 32, "one thread per id of a batch");
+
+  // per-lane shared addresses used by the warp reduction (computed once)
+  const uint32_t w_base = smem_u32(s_w + warp * 9 * WROW);
+  const uint32_t w_st = w_base + 4 * lane;                 // this lane's column in each of the 9 rows
+  const uint32_t w_sh = w_base + 4 * (16 * half);          // SH GEMV: 16 pixels of this lane's half
+  const int sv_row = lane >> 2, sv_q = lane & 3;           // scalar sums: row 3 + sv_row, quarter sv_q
+  const uint32_t w_sc = w_base + 4 * ((3 + (sv_row < 6 ? sv_row : 0)) * WROW + 8 * sv_q);
+  const uint32_t acc_warp = DIRECT ? 4 * (warp * ROWP) : 4 * (warp * B * ROWP);
+
+  // prologue: ids of batch 0 -> ring slot 0, batch 0 in flight, ids of batch 1 -> ring slot 1
+  if (id_lane) s_ids[threadIdx.x] = threadIdx.x < n_this ? ids[threadIdx.x] : 0;
+  int my_id = (id_lane && B + threadIdx.x < n_this) ? ids[B + threadIdx.x] : 0;
+  __syncthreads();  // ids visible, accumulators zeroed, basis transposition done
+  stage_batch<CC, B, NT>(p, s_ids, min(B, n_this), s_rec, s_sh);
+  cp_async_commit();
+  if (id_lane) s_ids[B + threadIdx.x] = my_id;
+  my_id = (id_lane && 2 * B + threadIdx.x < n_this) ? ids[2 * B + threadIdx.x] : 0;
+
+  for (int cb = 0;; ++cb) {
+    cp_async_wait<0>();
+    // one barrier per batch: batch cb has landed, every warp is done with batch cb-1, ring slot
+    // published; the vote ends the tile when every pixel is saturated
+    const bool stop = __syncthreads_and(dead != 0.0f) || cb == n_batches;
+    const int buf = cb & 1;
+    if (!stop && cb + 1 < n_batches) {
+      const int nbuf = buf ^ 1;
+      stage_batch<CC, B, NT>(p, s_ids + ((cb + 1) & 3) * B, min(B, n_this - (cb + 1) * B), s_rec + nbuf * B * 3,
+                             s_sh + nbuf * B * SHF);
+      cp_async_commit();
+    }
+    // flush of the previous batch (complete: every warp passed the barrier above after it)
+    if constexpr (!DIRECT) {
+      if (cb > 0) flush_batch2<CC, B, NW>(p, s_acc + (buf ^ 1) * ACC, s_ids + ((cb - 1) & 3) * B, B);
+    }
+    if (stop) {  // batches 0..cb were staged (all of them when cb == n_batches)
+      if (p.stats && threadIdx.x == 0 && sub == 0)
+        atomicAdd(p.stats + 1, (unsigned long long)min(n_this, (cb + 1) * B));
+      break;
+    }
+    const int nb = min(B, n_this - cb * B);
+    {
+      uint32_t rec_a = smem_u32(s_rec + buf * B * 3);
+      uint32_t sh_a = smem_u32(s_sh + buf * B * SHF);
+      uint32_t row_a = smem_u32(s_acc + (DIRECT ? 0 : buf * ACC)) + acc_warp;
+      const int *ids_b = s_ids + (cb & 3) * B;
+      for (int j = 0; j < nb; j += UB, rec_a += 48 * UB, sh_a += 4 * SHF * UB, row_a += DIRECT ? 0 : 4 * ROWP * UB) {
+       if (!__any_sync(FULL, dead == 0.0f)) break;
+#pragma unroll
+       for (int uu = 0; uu < UB; ++uu) {
+        float pw, df;
+        const float4 r1 = lds128(rec_a + 48 * uu + 16);
+        const float4 r0 = pair_test(px, py, rec_a + 48 * uu, pw, df);
+        // ---- decisions, as votes.  `dead` is 0 for a live pixel and 1e30 for a finished one.
+        const bool cand = !(df - dead < -DECISION_MARGIN) && dead == 0.0f;
+        bool contrib;
+        float G = ex2_approx(pw);
+        if constexpr (EXACT) {
+          contrib = cand && df >= DECISION_MARGIN && pw <= -1e-5f;  // far from the threshold: decided
+          const bool near_thr = cand && !contrib;                   // rare: the reference's arithmetic decides
+          if (__any_sync(FULL, near_thr)) {
+            if (near_thr) {
+              const float val = RGB ? gaussian_exact_f64(px - r0.x, py - r0.y, lds128(rec_a + 48 * uu + 32))
+                                    : gaussian_exact(px - r0.x, py - r0.y, lds128(rec_a + 48 * uu + 32));
+              G = val;
+              contrib = !(r0.z * val < MIN_RENDER_ALPHA);
+            }
+          }
+        } else {
+          contrib = cand && df >= 0.0f && !(pw > 0.0f);
+        }
+        if (!__any_sync(FULL, contrib)) continue;
+        G = contrib ? G : 0.0f;
+        // ---- straight-line for the whole warp (G = 0 makes a lane's contribution exactly zero)
+        const float a = r0.z;
+        const float aG = a * G;
+        float coeff = (a * T) * G;
+        if (!RGB && isnan(coeff)) coeff = 0.0f;
+        float y[3];
+        sh_colour<CC, RGB>(sh_a + 4 * SHF * uu, Y, y);
+        f0 = fmaf(-coeff, y[0], f0);
+        f1 = fmaf(-coeff, y[1], f1);
+        f2 = fmaf(-coeff, y[2], f2);
+        float w0, w1, w2;
+        if constexpr (RGB) {  // vol_render.h:305-307: grad_color += a T G * grad_out
+          w0 = coeff * g0; w1 = coeff * g1; w2 = coeff * g2;
+        } else {              // vol_render_sh.h:328-333
+          w0 = coeff * (y[0] * (1.0f - y[0])) * g0;
+          w1 = coeff * (y[1] * (1.0f - y[1])) * g1;
+          w2 = coeff * (y[2] * (1.0f - y[2])) * g2;
+        }
+        // vol_render_sh.h:336-342
+        const float one_m = 1.0f - aG;
+        const float inv1m = -rcp_approx(one_m);
+        float P = g0 * fmaf(y[0], T, f0 * inv1m);
+        P = fmaf(g1, fmaf(y[1], T, f1 * inv1m), P);
+        P = fmaf(g2, fmaf(y[2], T, f2 * inv1m), P);
+        // kernels.h:394-418 with the inverse covariance recovered from the conic
+        const float dx = px - r0.x, dy = py - r0.y;
+        const float i00 = r1.x * INV_K, i11 = r1.z * INV_K, i01 = (-0.5f * INV_K) * r1.y;
+        const float vx = fmaf(dx, i00, -dy * i01), vy = fmaf(dy, i11, -dx * i01);
+        const float gam = P * aG;
+        const float gmx = gam * vx, gmy = gam * vy;
+        const float hg = 0.5f * gam;
+        const float g00 = hg * vx * vx, g01 = hg * vx * vy, g11 = hg * vy * vy;
+        const float ga = P * G;
+        T *= one_m;
+        if (T < thresh) dead = DEAD;  // vol_render_sh.h:296-298 (T only changes here)
+        // ---- warp reduction over the 32 pixels through shared memory
+        sts32(w_st + 4 * 0 * WROW, w0);
+        sts32(w_st + 4 * 1 * WROW, w1);
+        sts32(w_st + 4 * 2 * WROW, w2);
+        sts32(w_st + 4 * 3 * WROW, gmx);
+        sts32(w_st + 4 * 4 * WROW, gmy);
+        sts32(w_st + 4 * 5 * WROW, g00);
+        sts32(w_st + 4 * 6 * WROW, g01);
+        sts32(w_st + 4 * 7 * WROW, g11);
+        sts32(w_st + 4 * 8 * WROW, ga);
+        __syncwarp();
+        f32x2 A0 = 0ull, A1 = 0ull, A2 = 0ull;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          f32x2 lo, hi;
+          lds128_2(w_sh + 16 * q, lo, hi);
+          A0 = fma2(lo, Yt[2 * q], A0);
+          A0 = fma2(hi, Yt[2 * q + 1], A0);
+          lds128_2(w_sh + 4 * WROW + 16 * q, lo, hi);
+          A1 = fma2(lo, Yt[2 * q], A1);
+          A1 = fma2(hi, Yt[2 * q + 1], A1);
+          lds128_2(w_sh + 8 * WROW + 16 * q, lo, hi);
+          A2 = fma2(lo, Yt[2 * q], A2);
+          A2 = fma2(hi, Yt[2 * q + 1], A2);
+        }
+        float a0 = sum2(A0), a1 = sum2(A1), a2 = sum2(A2);
+        // six scalar sums: lane = 4*v + qd sums pixels 8*qd .. 8*qd+7 of row 3+v
+        float sv;
+        {
+          const float4 x0 = lds128(w_sc), x1 = lds128(w_sc + 16);
+          sv = ((x0.x + x0.y) + (x0.z + x0.w)) + ((x1.x + x1.y) + (x1.z + x1.w));
+        }
+        __syncwarp();
+        a0 += __shfl_xor_sync(FULL, a0, 16);
+        a1 += __shfl_xor_sync(FULL, a1, 16);
+        a2 += __shfl_xor_sync(FULL, a2, 16);
+        sv += __shfl_xor_sync(FULL, sv, 1);
+        sv += __shfl_xor_sync(FULL, sv, 2);
+        const uint32_t ra = row_a + (DIRECT ? 0 : 4 * ROWP * uu);
+        if (lane < KL) {  // this (warp, Gaussian) row is written once per batch: plain stores
+          sts32(ra + 4 * lane, a0);
+          sts32(ra + 4 * (CC + lane), a1);
+          sts32(ra + 4 * (2 * CC + lane), a2);
+        }
+        if (sv_q == 0 && sv_row < 6) sts32(ra + 4 * (SHF + sv_row), sv);
+        if constexpr (DIRECT) {
+          __syncwarp();
+          if (lane < NQ) {
+            const float4 q4 = lds128(ra + 16 * lane);
+            if (!(q4.x == 0.f && q4.y == 0.f && q4.z == 0.f && q4.w == 0.f)) {
+              const size_t g = (size_t)ids_b[j + uu];
+              if (lane == 0 && p.touched) p.touched[g] = 1;
+              emit_quad<CC>(p, g, lane, q4);
+            }
+          }
+          __syncwarp();
+        }
+       }
+      }
+    }
+    if (cb + 1 < n_batches) {
+      if (id_lane) s_ids[((cb + 2) & 3) * B + threadIdx.x] = my_id;
+      const int nxt = (cb + 3) * B + threadIdx.x;
+      my_id = (id_lane && nxt < n_this) ? ids[nxt] : 0;
+    }
+  }
+  cp_async_wait<0>();
+}
+
+
 // ---------------------------------------------------------------- host side
 
 template <int C, int B>
@@ -789,6 +1126,14 @@ static size_t bwd_smem() {
   return (size_t)2 * B * 3 * sizeof(float4) + (size_t)2 * B * 3 * C * C * sizeof(float) +
          (size_t)NWARPS * 9 * WROW * sizeof(float) + (size_t)2 * NWARPS * B * ROWP * sizeof(float) +
          (size_t)4 * B * sizeof(int);
+}
+
+template <int C, int B, int NW, bool DIRECT>
+static size_t bwd2_smem() {
+  constexpr int ROWP = (3 * C * C + 6 + 3) & ~3;
+  return (size_t)2 * B * 3 * sizeof(float4) + (size_t)2 * B * 3 * C * C * sizeof(float) +
+         (size_t)NW * 9 * WROW * sizeof(float) +
+         (DIRECT ? (size_t)NW * ROWP : (size_t)2 * NW * B * ROWP) * sizeof(float) + (size_t)4 * B * sizeof(int);
 }
 
 constexpr int FWD_B = 64;
@@ -821,8 +1166,32 @@ static int launch_bwd_t(const CompositeParams &p, uint32_t n_tiles, cudaStream_t
   GS3D_LAUNCH_CHECK();
   return GS3D_OK;
 }
+template <int C, int B, bool EXACT, bool RGB, int NW, bool DIRECT>
+static int launch_bwd2_t(const CompositeParams &p, uint32_t n_tiles, cudaStream_t st) {
+  size_t sm = bwd2_smem<C, B, NW, DIRECT>();
+  GS3D_CUDA(cudaFuncSetAttribute(composite_bwd2_kernel<C, B, EXACT, RGB, NW, DIRECT>,
+                                 cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+  composite_bwd2_kernel<C, B, EXACT, RGB, NW, DIRECT><<<n_tiles * (8 / NW), NW * 32, sm, st>>>(p);
+  GS3D_LAUNCH_CHECK();
+  return GS3D_OK;
+}
+
 template <int C>
 static int launch_bwd(const CompositeParams &p, uint32_t n_tiles, cudaStream_t st) {
+#ifdef GS3D_BWD_EXPERIMENTS  // A/B builds (tools/ablate.sh): GS3D_BWD_VARIANT picks the kernel at run time
+  if constexpr (C == 4) {
+    static const int variant = env_int("GS3D_BWD_VARIANT", 0);
+    if (p.exact) switch (variant) {
+      case 1: return launch_bwd2_t<4, 16, true, false, 8, false>(p, n_tiles, st);  // uniform flow, accumulators
+      case 2: return launch_bwd2_t<4, 64, true, false, 8, true>(p, n_tiles, st);   // direct, barrier per 64
+      case 3: return launch_bwd2_t<4, 32, true, false, 8, true>(p, n_tiles, st);   // direct, barrier per 32
+      case 4: return launch_bwd2_t<4, 16, true, false, 4, false>(p, n_tiles, st);  // half tiles, accumulators
+      case 5: return launch_bwd2_t<4, 64, true, false, 4, true>(p, n_tiles, st);   // half tiles, direct
+      case 6: return launch_bwd2_t<4, 32, true, false, 4, false>(p, n_tiles, st);  // half tiles, accumulators, 32
+      default: break;
+    }
+  }
+#endif
   // batch of 16 Gaussians -> 45 KB of shared memory and <= 85 registers: three CTAs per SM hide the
   // barrier / warp-imbalance stalls better than two CTAs with 32 (measured: 1.45 vs 1.57 ms, cfg 2).
   static const int bb = env_int("GS3D_BWD_B", 16);

@@ -151,52 +151,95 @@ struct Projected {
   float m2[2];   // mean2d
 };
 
-// gs/renderer.py:381-419 restated per Gaussian (summation order j = 0,1,2 like a batched GEMM).
+// ---- rounding-exact building blocks.  The reference computes the projection with ATen / cuBLAS kernels
+// (gs/renderer.py:381-419).  tools/probe_torch_order.py measured, on a B200 with torch 2.11, where those
+// kernels round (profiles/r2_probe_torch_order.json, 1 M Gaussians, identity and posed camera, 100 % bit match):
+//   * every small matrix product (the einsum of project_pts and of JW, `rotmat @ rotmat^T`, both bmm of the
+//     covariance) accumulates k = 0,1,2 as  fma(a2, b2, fma(a1, b1, a0 * b0));
+//   * torch.norm(u, dim=-1) of the Jacobian is sqrt((u0^2 + u2^2) + u1^2), products rounded separately;
+//   * F.normalize(q) (kornia's normalize_quaternion) is q / max(sqrt((q0^2 + q2^2) + (q1^2 + q3^2)), eps);
+//   * everything else is one rounding per torch op.
+// project_one reproduces exactly that with un-contracted intrinsics, so that the 2-D covariance -- and with
+// it tile rects, duplicate counts and the 1/255 skip decisions -- is bit-identical to the reference flow.
+__device__ __forceinline__ float xmul(float a, float b) { return __fmul_rn(a, b); }
+__device__ __forceinline__ float xadd(float a, float b) { return __fadd_rn(a, b); }
+__device__ __forceinline__ float xsub(float a, float b) { return __fsub_rn(a, b); }
+__device__ __forceinline__ float xdiv(float a, float b) { return __fdiv_rn(a, b); }
+__device__ __forceinline__ float dot3_gemm(float a0, float b0, float a1, float b1, float a2, float b2) {
+  return __fmaf_rn(a2, b2, __fmaf_rn(a1, b1, __fmul_rn(a0, b0)));
+}
+
+// kornia 0.6.x quaternion_to_rotation_matrix(q, WXYZ) op for op (utils/transforms.py:31-45 -> kornia,
+// un-vendored): normalize_quaternion, then the t* product form, one rounding per torch op.
+__device__ __forceinline__ void quat_to_rotmat_exact(const float *q, float *R, float *qn, float *inv_norm) {
+  const float n = __fsqrt_rn(xadd(xadd(xmul(q[0], q[0]), xmul(q[2], q[2])), xadd(xmul(q[1], q[1]), xmul(q[3], q[3]))));
+  const float d = fmaxf(n, 1e-12f);
+  const float w = xdiv(q[0], d), x = xdiv(q[1], d), y = xdiv(q[2], d), z = xdiv(q[3], d);
+  const float tx = xmul(2.0f, x), ty = xmul(2.0f, y), tz = xmul(2.0f, z);
+  const float twx = xmul(tx, w), twy = xmul(ty, w), twz = xmul(tz, w);
+  const float txx = xmul(tx, x), txy = xmul(ty, x), txz = xmul(tz, x);
+  const float tyy = xmul(ty, y), tyz = xmul(tz, y), tzz = xmul(tz, z);
+  R[0] = xsub(1.0f, xadd(tyy, tzz));
+  R[1] = xsub(txy, twz);
+  R[2] = xadd(txz, twy);
+  R[3] = xadd(txy, twz);
+  R[4] = xsub(1.0f, xadd(txx, tzz));
+  R[5] = xsub(tyz, twx);
+  R[6] = xsub(txz, twy);
+  R[7] = xadd(tyz, twx);
+  R[8] = xsub(1.0f, xadd(txx, tyy));
+  qn[0] = w; qn[1] = x; qn[2] = y; qn[3] = z;
+  *inv_norm = 1.0f / d;  // (backward only; not on the bit-exact forward path)
+}
+
+// gs/renderer.py:381-419 restated per Gaussian, rounding where the reference's GPU kernels round (see above).
 __device__ __forceinline__ void project_one(const float *p, const float *q, const float *s,
                                             const float *c2w, Projected &o) {
-  // project_pts: W = c2w[:3,:3]^T, d = -t, u = W (p + d)
+  // project_pts: W = c2w[:3,:3]^T, d = -t, u = einsum("ij,bj->bi", W, p + d)
   float pd[3];
 #pragma unroll
-  for (int j = 0; j < 3; ++j) pd[j] = p[j] + (-c2w[4 * j + 3]);
+  for (int j = 0; j < 3; ++j) pd[j] = xadd(p[j], -c2w[4 * j + 3]);
 #pragma unroll
   for (int i = 0; i < 3; ++i)
-    o.u[i] = c2w[4 * 0 + i] * pd[0] + c2w[4 * 1 + i] * pd[1] + c2w[4 * 2 + i] * pd[2];
-  quat_to_rotmat(q[0], q[1], q[2], q[3], o.R, o.qn, &o.qinv);
-  // rotmat = svec.unsqueeze(-2) * R  ->  A[i][j] = R[i][j] * s[j];  sigma = A A^T
+    o.u[i] = dot3_gemm(c2w[4 * 0 + i], pd[0], c2w[4 * 1 + i], pd[1], c2w[4 * 2 + i], pd[2]);
+  quat_to_rotmat_exact(q, o.R, o.qn, &o.qinv);
+  // rotmat = svec.unsqueeze(-2) * R  ->  A[i][j] = s[j] * R[i][j];  sigma = A @ A^T
   float A[9], Sg[9];
 #pragma unroll
   for (int i = 0; i < 3; ++i)
 #pragma unroll
-    for (int j = 0; j < 3; ++j) A[3 * i + j] = o.R[3 * i + j] * s[j];
+    for (int j = 0; j < 3; ++j) A[3 * i + j] = xmul(s[j], o.R[3 * i + j]);
 #pragma unroll
   for (int i = 0; i < 3; ++i)
 #pragma unroll
     for (int j = 0; j < 3; ++j)
-      Sg[3 * i + j] = A[3 * i] * A[3 * j] + A[3 * i + 1] * A[3 * j + 1] + A[3 * i + 2] * A[3 * j + 2];
+      Sg[3 * i + j] = dot3_gemm(A[3 * i], A[3 * j], A[3 * i + 1], A[3 * j + 1], A[3 * i + 2], A[3 * j + 2]);
   // jacobian (renderer.py:366-377)
-  float ux = o.u[0], uy = o.u[1], uz = o.u[2];
-  float l = sqrtf(ux * ux + uy * uy + uz * uz);
-  float J[9] = {1.0f / uz, 0.0f, -ux / uz / uz, 0.0f, 1.0f / uz, -uy / uz / uz, ux / l, uy / l, uz / l};
-  // JW = J @ W, W[j][k] = c2w[k][j]
+  const float ux = o.u[0], uy = o.u[1], uz = o.u[2];
+  const float l = __fsqrt_rn(xadd(xadd(xmul(ux, ux), xmul(uz, uz)), xmul(uy, uy)));
+  const float inv_z = xdiv(1.0f, uz);
+  const float J[9] = {inv_z, 0.0f, xdiv(xdiv(-ux, uz), uz), 0.0f, inv_z, xdiv(xdiv(-uy, uz), uz),
+                      xdiv(ux, l), xdiv(uy, l), xdiv(uz, l)};
+  // JW = einsum("bij,jk->bik", J, W), W[j][k] = c2w[k][j]
 #pragma unroll
   for (int i = 0; i < 3; ++i)
 #pragma unroll
     for (int k = 0; k < 3; ++k)
-      o.JW[3 * i + k] = J[3 * i] * c2w[4 * k + 0] + J[3 * i + 1] * c2w[4 * k + 1] + J[3 * i + 2] * c2w[4 * k + 2];
-  // cov = (JW sigma JW^T)[:2,:2]
+      o.JW[3 * i + k] = dot3_gemm(J[3 * i], c2w[4 * k + 0], J[3 * i + 1], c2w[4 * k + 1], J[3 * i + 2], c2w[4 * k + 2]);
+  // cov = bmm(bmm(JW, sigma), JW^T)[:2,:2]
   float X[6];
 #pragma unroll
   for (int a = 0; a < 2; ++a)
 #pragma unroll
     for (int k = 0; k < 3; ++k)
-      X[3 * a + k] = o.JW[3 * a] * Sg[k] + o.JW[3 * a + 1] * Sg[3 + k] + o.JW[3 * a + 2] * Sg[6 + k];
+      X[3 * a + k] = dot3_gemm(o.JW[3 * a], Sg[k], o.JW[3 * a + 1], Sg[3 + k], o.JW[3 * a + 2], Sg[6 + k]);
 #pragma unroll
   for (int a = 0; a < 2; ++a)
 #pragma unroll
     for (int b = 0; b < 2; ++b)
-      o.S[2 * a + b] = X[3 * a] * o.JW[3 * b] + X[3 * a + 1] * o.JW[3 * b + 1] + X[3 * a + 2] * o.JW[3 * b + 2];
-  o.m2[0] = ux / uz;
-  o.m2[1] = uy / uz;
+      o.S[2 * a + b] = dot3_gemm(X[3 * a], o.JW[3 * b], X[3 * a + 1], o.JW[3 * b + 1], X[3 * a + 2], o.JW[3 * b + 2]);
+  o.m2[0] = xdiv(ux, uz);
+  o.m2[1] = xdiv(uy, uz);
 }
 
 __global__ void __launch_bounds__(256)

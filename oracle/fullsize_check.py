@@ -9,6 +9,7 @@ the GPU) feeding the REAL reference CUDA extension (oracle/_ref/_gs_ref*.so).
 Reported per workload (all counts are over the whole scene, nothing sampled):
   mask_mismatch        frustum-cull decisions that differ
   n_dub_ours / _ref    duplicate counts (must be equal)
+  bits_{svec,alpha}    activated scales / opacities not BIT-identical to torch.exp / torch.sigmoid on the GPU
   bits_{mean2d,cov,depth}   Gaussians whose projected values are not BIT-identical to the reference's
   rect_mismatch        Gaussians whose integer tile rect differs (target 0: SURVEY hard-part 2)
   ranges_equal         start/end arrays identical
@@ -110,7 +111,10 @@ def compare_whole_path(ext, name, N=None, seed=0, backward=True, device="cuda:0"
     from gaussian_splatting_3d_b200 import ops
 
     k1 = ops.project_cull_fused(r.mean.data, r.qvec.data, r.svec_before_activation.data, r.alpha_before_activation.data,
-                                1, 1, c2w, cam, 1.0, False, 6.0, 16, want_records=False, want_activated=False)
+                                1, 1, c2w, cam, 1.0, False, 6.0, 16, want_records=False, want_activated=True)
+    # activations (sh_renderer.py:318-324: torch.exp / torch.sigmoid on the GPU) against the fused kernel's
+    res["bits_svec"] = _bits_differ(k1["svec"], torch.exp(r.svec_before_activation.data))
+    res["bits_alpha"] = _bits_differ(k1["alpha"].view(-1, 1), torch.sigmoid(r.alpha_before_activation.data).view(-1, 1))
     res["mask_mismatch"] = int((k1["mask"] != m).sum())
     res["n_dub_ours"], res["n_dub_ref"] = int(r.total_dub_gaussians), ref_keep["n_dub"]
     both = k1["mask"] & m
@@ -168,7 +172,7 @@ def compare_whole_path(ext, name, N=None, seed=0, backward=True, device="cuda:0"
 
 
 def summarize(res):
-    keys = ("workload", "N", "n_dub_ours", "n_dub_ref", "mask_mismatch", "bits_mean2d", "bits_cov", "bits_depth",
+    keys = ("workload", "N", "n_dub_ours", "n_dub_ref", "mask_mismatch", "bits_svec", "bits_alpha", "bits_mean2d", "bits_cov", "bits_depth",
             "rect_mismatch", "ranges_equal", "keys_equal", "ids_tie_only", "image_max_abs", "image_gt_1e4")
     s = ", ".join(f"{k}={res[k]}" for k in keys if k in res)
     g = ", ".join(f"{k[5:]}={res[k]:.2e}" for k in sorted(res) if k.startswith("grad_"))
