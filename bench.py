@@ -33,7 +33,13 @@ def parse():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="cfg2", choices=["cfg1", "cfg2", "cfg3", "cfg5"])
+    ap.add_argument("--workload", default="cfg2", choices=["cfg1", "cfg2", "cfg3", "cfg4", "cfg5"],
+                    help="cfg2 (default): one view per rank per step, weak scaling.  cfg4 (SURVEY 8d): the cfg-2 scene, "
+                         "8 ring cameras per step, 8/G cameras per rank, gradients exchanged -- strong scaling.  cfg5: "
+                         "6 M Gaussians at 3840x2160, forward only, tile rows sharded over the ranks -- strong scaling")
+    ap.add_argument("--check", action="store_true",
+                    help="after timing: whole-path parity of this workload against the reference GPU flow "
+                         "(oracle/fullsize_check.py; needs oracle/_ref) added to the line as `parity`")
     ap.add_argument("--n-gaussians", type=int, default=None, help="override N (debugging)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-exact", action="store_true", help="disable exact skip decisions")
@@ -135,6 +141,14 @@ def dp_exchange_desc(flat, world, N):
     return "dense 708 MB NCCL all-reduce"
 
 
+def workload_desc(name, N, C, cam, views_per_step):
+    """The same string in both arms (the driver compares `config` of the two lines)."""
+    if name == "cfg5":
+        return f"cfg5: {N} Gaussians, SH degree {C - 1} (C={C}), {cam.w}x{cam.h}, forward only"
+    what = "8 ring cameras per step (radius 7 around (0,0,7))" if name == "cfg4" else "1 view/step/GPU"
+    return f"{name}: {N} Gaussians, SH degree {C - 1} (C={C}), {cam.w}x{cam.h}, {what}, fwd + L2 loss + bwd"
+
+
 def peaks():
     p = ROOT / "MEASURED_PEAKS.json"
     if p.exists():
@@ -176,6 +190,47 @@ def cpu_baseline(args, scene_name, seed=0):
             "fwd_fps": 1.0 / ((t1 - t0) * scale)}
 
 
+# ---------------------------------------------------------------- multi-GPU checks and side workloads
+
+def exchange_check(flat, step_once, torch, dist):
+    """Run ONE more step and compare the exchanged gradient buffer with a dense NCCL all-reduce of the ranks'
+    own contributions of that same step -> max over ranks of ||exchanged - dense|| / ||dense||."""
+    own = {}
+    orig = flat.exchange
+
+    def spy(*a, **k):
+        # this rank's contribution: the private rows (push / pull), else the not yet reduced flat buffer
+        src = flat.local if flat.local is not None else flat.flat
+        own["g"] = src.detach().clone()
+        return orig(*a, **k)
+
+    if flat.fused:
+        return None  # the SH block is reduced inside the backward kernel: no separate own contribution exists
+    flat.exchange = spy
+    try:
+        step_once()
+    finally:
+        del flat.exchange
+    torch.cuda.synchronize()
+    dense = own["g"]
+    dist.all_reduce(dense, op=dist.ReduceOp.SUM)
+    num = (flat.flat.double() - dense.double()).norm()
+    den = dense.double().norm().clamp_min(1e-30)
+    rel = (num / den).float().reshape(1)
+    dist.all_reduce(rel, op=dist.ReduceOp.MAX)
+    return float(rel.item())
+
+
+def union_rows_of_last_exchange(flat, torch):
+    """Rows (Gaussians) whose gradients crossed NVLink in the last exchange, and the bytes each GPU ingested."""
+    if flat is None or not flat.push:
+        return None, None
+    used = flat._res[flat._cur ^ 1]  # exchange() flipped the buffers
+    U = int((used["union"] != 0).sum().item())
+    row_bytes = 4 * sum(v.numel() // v.size(0) for v in flat.views)
+    return U, U * row_bytes + int(used["union"].numel())
+
+
 # ---------------------------------------------------------------- our arm
 
 def run_ours(args, rank, local_rank, world):
@@ -190,17 +245,32 @@ def run_ours(args, rank, local_rank, world):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     name = args.workload
-    cam = S.make_camera(name)
-    sc = S.make_scene(name, seed=0, N=args.n_gaussians)
+    if name == "cfg5":
+        return run_cfg5(args, rank, local_rank, world, dev)
+    cfg4 = name == "cfg4"
+    scene = "cfg2" if cfg4 else name  # cfg 4 = the cfg-2 scene seen from 8 ring cameras
+    cam = S.make_camera(scene)
+    sc = S.make_scene(scene, seed=0, N=args.n_gaussians)
     C = sc["C"]
     cfg = S.make_cfg(device=str(dev), sh_order=C, exact_decisions=not args.no_exact)
     r = S.renderer_from_scene(sc, cfg)
     r.train()
     N = r.N
-    c2w_host = views_for(world, torch)[rank].pin_memory()
-    tgt_host = S.make_target(cam, rank).pin_memory()
-    c2w_dev = c2w_host.to(dev)
-    tgt_dev = tgt_host.to(dev)
+    if cfg4:
+        from gaussian_splatting_3d_b200 import parallel as P
+
+        ring = S.ring_cameras(8)
+        my_views = P.shard_views(8, rank, world)  # 8/G cameras per rank, round-robin
+        c2w_hosts = [ring[i].pin_memory() for i in my_views]
+        tgt_hosts = [S.make_target(cam, i).pin_memory() for i in my_views]
+        n_views_step = 8
+    else:
+        c2w_hosts = [views_for(world, torch)[rank].pin_memory()]
+        tgt_hosts = [S.make_target(cam, rank).pin_memory()]
+        n_views_step = world
+    c2w_devs = [c.to(dev) for c in c2w_hosts]
+    tgt_devs = [t.to(dev) for t in tgt_hosts]
+    c2w_dev = c2w_devs[0]
     params = [r.mean, r.qvec, r.svec_before_activation, r.sh_coeffs, r.alpha_before_activation]
     flat = None
     if world == 1:
@@ -222,31 +292,36 @@ def run_ours(args, rank, local_rank, world):
     copy_stream = torch.cuda.Stream(device=dev)
 
     def step(e2e):
-        tgt_ready = None
-        if e2e:
-            # the pose (48 B) is needed by the first kernel: current stream.  The 13 MB target image is not
-            # needed before the loss: its host->device copy runs on a copy stream beside the forward kernels
-            c2w = c2w_host.to(dev, non_blocking=True)
-            main = torch.cuda.current_stream(dev)
-            copy_stream.wait_stream(main)  # (the previous step's consumers of the recycled block are done)
-            with torch.cuda.stream(copy_stream):
-                tgt = tgt_host.to(dev, non_blocking=True)
-                tgt_ready = torch.cuda.Event()
-                tgt_ready.record(copy_stream)
-            tgt.record_stream(main)
-        else:
-            c2w, tgt = c2w_dev, tgt_dev
         flat.zero()  # per-step reset of the gradient buffers (N > 1: side stream, overlaps the forward)
-        out = r(c2w, cam)
-        if tgt_ready is not None:
-            torch.cuda.current_stream(dev).wait_event(tgt_ready)
-        loss = ((out - tgt) ** 2).mean()
-        flat.backward_into(loss)
+        total = None
+        for v in range(len(c2w_devs)):
+            tgt_ready = None
+            if e2e:
+                # the pose (48 B) is needed by the first kernel: current stream.  The 13 MB target image is not
+                # needed before the loss: its host->device copy runs on a copy stream beside the forward kernels
+                c2w = c2w_hosts[v].to(dev, non_blocking=True)
+                main = torch.cuda.current_stream(dev)
+                copy_stream.wait_stream(main)  # (the previous consumers of the recycled block are done)
+                with torch.cuda.stream(copy_stream):
+                    tgt = tgt_hosts[v].to(dev, non_blocking=True)
+                    tgt_ready = torch.cuda.Event()
+                    tgt_ready.record(copy_stream)
+                tgt.record_stream(main)
+            else:
+                c2w, tgt = c2w_devs[v], tgt_devs[v]
+            out = r(c2w, cam)
+            if tgt_ready is not None:
+                torch.cuda.current_stream(dev).wait_event(tgt_ready)
+            loss = ((out - tgt) ** 2).mean()
+            flat.backward_into(loss)  # accumulates into the flat buffer
+            total = loss.detach() if total is None else total + loss.detach()
         if world > 1:
             flat.exchange()
+            if cfg4:  # a training step: the ADC statistics follow the gradients (parallel.view_sharded_step)
+                P.sync_adc(r)
         if e2e:
-            return float(loss.item())  # device -> host read of the step's result
-        return loss
+            return float(total.item())  # device -> host read of the step's result
+        return total
 
     def fwd_only():
         with torch.no_grad():
@@ -322,18 +397,25 @@ def run_ours(args, rank, local_rank, world):
     n_prof = min(args.steps, 10)
     # units the compositing launches really process: duplicates STAGED into shared memory (tiles stop
     # staging once every pixel is saturated), counted by the kernels themselves during these steps
-    staged = torch.zeros(2, dtype=torch.int64, device=dev)
+    for _ in range(n_prof):  # per-stage times: the production kernels
+        step(False)
+    torch.cuda.synchronize()
+    # unit counts (separate steps: launches made while the counters are set run the instrumented kernels)
+    staged = torch.zeros(4, dtype=torch.int64, device=dev)
     ops.set_stage_counters(staged)
-    for _ in range(n_prof):
+    n_cnt = 2
+    for _ in range(n_cnt):
         step(False)
     torch.cuda.synchronize()
     ops.set_stage_counters(None)
-    staged_fwd, staged_bwd = (int(x) // n_prof for x in staged.tolist())
+    staged_fwd, staged_bwd, pairs_fwd, pairs_bwd = (int(x) // n_cnt for x in staged.tolist())
     for fname, f in orig.items():
         setattr(ops, fname, f)
     if flat is not None and world > 1:
         del flat.zero, flat.exchange  # drop the instance-level wrappers
-    kernels_ms = {k: sum(a.elapsed_time(b) for a, b in v) / n_prof for k, v in stage_ms.items()}  # per step
+    # per step, over the first n_prof (un-instrumented) steps
+    per_step = {k: len(v) // (n_prof + n_cnt) for k, v in stage_ms.items()}
+    kernels_ms = {k: sum(a.elapsed_time(b) for a, b in v[:per_step[k] * n_prof]) / n_prof for k, v in stage_ms.items()}
 
     rank_kernel_ms = None
     if world > 1:  # per-rank sum of the hot-path kernels: shows how uneven the views' work is
@@ -343,78 +425,232 @@ def run_ours(args, rank, local_rank, world):
         rank_kernel_ms = [round(float(t.item()), 4) for t in allr]
     n_dub = r.total_dub_gaussians
     ms_step = ms_total / args.steps
-    value = world * 1000.0 / ms_step
-    hbm_peak, peak_src = peaks()
-    CC = C * C
-    # algorithmic bytes per launch of the dominant kernel (DESIGN.md "Kernels"): per STAGED
-    # duplicate 4 (id) + 48 (record) + 12*C^2 (SH row); per pixel 12 (image) [+ 24 read in backward];
-    # backward adds one gradient row reduction of 4*(7+3C^2) B per staged duplicate at most (rows of
-    # Gaussians that contributed nothing are skipped).  `upper_bound` is the same with all n_dub staged.
-    px = cam.w * cam.h
-    per_dup = 4 + 48 + 12 * CC
-    bytes_fwd = staged_fwd * per_dup + px * 12
-    bytes_bwd = staged_bwd * (per_dup + 4 * (7 + 3 * CC)) + px * 36
-    upper = {"K3_composite_fwd": n_dub * per_dup + px * 12,
-             "K4a_composite_bwd": n_dub * (per_dup + 4 * (7 + 3 * CC)) + px * 36}
-    kk = {k: v for k, v in kernels_ms.items() if k.startswith("K")}
-    dom = max(kk, key=kk.get) if kk else None
-    algo = {"K3_composite_fwd": bytes_fwd, "K4a_composite_bwd": bytes_bwd, "K1_project_cull": N * (48 + 101),
-            "K2_binning": N * (4 + 4 * 24 + 8) + n_dub * (8 + 2 * 24 + 4), "K4b_project_bwd": N * (48 + 28 + 44 + 1)}
-    roofline = None
-    if dom:
-        ach = algo[dom] / (kernels_ms[dom] * 1e-3) / 1e9
-        traffic, traffic_src, issue = None, None, None
-        tfile = ROOT / "profiles" / "ncu_traffic.json"
-        if name == "cfg2" and args.n_gaussians is None and tfile.exists():
-            try:  # dram__bytes_read.sum + dram__bytes_write.sum of one ncu --set full capture of this workload
-                t = json.loads(tfile.read_text()).get(dom)
-                if t:
-                    traffic, traffic_src = t["traffic"], t["source"]
-                    # what actually bounds the compositing kernels (same capture): issue slots / pipes
-                    issue = {k: t[k] for k in ("issue_slot_pct", "fma_pipe_pct", "lsu_pipe_pct", "smem_wavefront_pct",
-                                               "warps_active_pct") if t.get(k) is not None}
-            except Exception:
-                pass
-        roofline = {"kernel": dom, "bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s",
-                    "frac": ach / hbm_peak, "traffic": traffic, "traffic_source": traffic_src,
-                    "peak_source": peak_src, "algorithmic_bytes": algo[dom], "launch_ms": kernels_ms[dom],
-                    "staged_duplicates": {"fwd": staged_fwd, "bwd": staged_bwd, "n_dub": n_dub},
-                    "ncu_utilisation_pct_of_peak": issue,
-                    "algorithmic_bytes_if_all_staged": upper.get(dom),
-                    "note": "compositing is FP32-issue / shared-memory bound, not HBM bound (DESIGN.md: ncu "
-                            "issue-slot utilisation 64-69 %, FMA pipe 42-47 %, DRAM < 2 %); algorithmic bytes "
-                            "count the duplicates actually staged (tiles stop once saturated) and are served "
-                            "mostly from L2 (a Gaussian is staged by ~3.7 tiles), hence traffic < algorithmic"}
+    value = n_views_step * 1000.0 / ms_step
+    rooflines, dom = stage_rooflines(kernels_ms, N=N, C=C, cam=cam, n_dub=n_dub, views=len(c2w_devs),
+                                     staged=(staged_fwd, staged_bwd), pairs=(pairs_fwd, pairs_bwd),
+                                     ncu_ok=(name == "cfg2" and args.n_gaussians is None),
+                                     touched_rows=(int((flat.touched != 0).sum().item())
+                                                   if flat is not None and flat.touched is not None else 0))
+    n_views_rank = len(c2w_devs)
+    h2d = sum(int(c.numel() * 4 + t.numel() * 4) for c, t in zip(c2w_hosts, tgt_hosts))
     line = {
         "metric": "fwd+bwd iters/s (3M Gaussians SH3 @1297x840)", "value": value, "unit": "iters/s",
         "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_step,
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"{name}: {N} Gaussians, SH degree {C - 1} (C={C}), {cam.w}x{cam.h}, "
-                               f"1 view/step/GPU, fwd + L2 loss + bwd", "n_dub": n_dub,
-                   "views_per_step": world, "parallelism": f"dp{world}" if world > 1 else "single",
-                   "dp_exchange": dp_exchange_desc(flat, world, N),
-                   "gradient_buffers": "one persistent flat buffer aliased by .grad; per-step reset clears only "
-                                       "the rows the previous backward marked",
-                   "l2_policy": "inputs larger than L2 (parameters 708 MB, duplicates 132 MB vs 126 MB L2)",
-                   "exact_decisions": not args.no_exact},
+        "higher_is_better": True, "scaling": "strong" if cfg4 else "weak", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic",
+        "config": {"workload": workload_desc(name, N, C, cam, n_views_step), "n_dub": n_dub,
+                   "views_per_step": n_views_step, "parallelism": f"dp{world}" if world > 1 else "single"},
+        "impl_details": {"views_per_rank": n_views_rank, "dp_exchange": dp_exchange_desc(flat, world, N),
+                         "gradient_buffers": "one persistent flat buffer aliased by .grad; per-step reset clears "
+                                             "only the rows the previous backward marked",
+                         "l2_policy": "inputs larger than L2 (parameters 708 MB, duplicates 132 MB vs 126 MB L2)",
+                         "exact_decisions": not args.no_exact},
         "fwd_fps": world * 1000.0 * args.steps / ms_fwd,
         "kernels_ms": kernels_ms,
         "rank_kernel_ms": rank_kernel_ms,
-        "roofline": roofline,
-        "e2e": {"value": world * 1000.0 * args.steps / ms_e2e, "unit": "iters/s",
-                "h2d_bytes_per_step": int(c2w_host.numel() * 4 + tgt_host.numel() * 4), "d2h_bytes_per_step": 4},
+        "roofline": rooflines.get(dom) if dom else None,
+        "rooflines": rooflines,
+        "e2e": {"value": n_views_step * 1000.0 * args.steps / ms_e2e, "unit": "iters/s",
+                "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4},
         "gpu_launches": int(launches),
         "clocks": clocks,
     }
+    if world > 1:
+        # correctness of the exchange, measured in this very run: one more step against a dense NCCL all-reduce
+        line["exchange_check"] = {"rel_err_vs_dense_allreduce": exchange_check(flat, lambda: step(False), torch, dist),
+                                  "tolerance": 1e-5}
+        U, ingest = union_rows_of_last_exchange(flat, torch)
+        line["exchange_union_rows"] = U
+        line["exchange_bytes_ingested_per_gpu"] = ingest
+        line["exchange_dense_bytes"] = int(flat.flat.numel() * 4)
+    if args.check and world == 1:
+        line["parity"] = parity_block(name, args, torch)
     if rank == 0:
         if world == 1 and not args.no_cpu_baseline:
             try:
-                line["cpu_baseline"] = cpu_baseline(args, name)
+                line["cpu_baseline"] = cpu_baseline(args, scene)
             except Exception as e:  # the baseline is a report, never a reason to lose the GPU number
                 line["cpu_baseline"] = {"error": str(e)}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+def run_cfg5(args, rank, local_rank, world, dev):
+    """cfg 5 (BASELINE configs[4]): 6 M Gaussians at 3840x2160, forward only, tile rows sharded over the ranks
+    (parallel.tile_sharded_render: replicated projection, per-rank band binning + compositing, bands gathered).
+    Strong scaling: value = frames/s of the SAME frame at N GPUs."""
+    import torch
+    import torch.distributed as dist
+
+    from gaussian_splatting_3d_b200 import capi
+    from gaussian_splatting_3d_b200 import parallel as P
+    from gaussian_splatting_3d_b200 import synthetic as S
+
+    name = "cfg5"
+    cam = S.make_camera(name)
+    sc = S.make_scene(name, seed=0, N=args.n_gaussians)
+    C = sc["C"]
+    r = S.renderer_from_scene(sc, S.make_cfg(device=str(dev), sh_order=C, exact_decisions=not args.no_exact))
+    r.eval()
+    c2w_host = sc["c2w"].pin_memory()
+    c2w_dev = c2w_host.to(dev)
+    frame_host = torch.empty(cam.h, cam.w, 3, dtype=torch.float32).pin_memory() if rank == 0 else None
+
+    def frame(e2e):
+        c2w = c2w_host.to(dev, non_blocking=True) if e2e else c2w_dev
+        img = P.tile_sharded_render(r, c2w, cam)
+        if e2e and rank == 0:  # what the viewer does with a frame (viser_viewer.py:119-139: `.cpu()`)
+            frame_host.copy_(img, non_blocking=True)
+            torch.cuda.current_stream(dev).synchronize()
+        return img
+
+    def timed(fn, k):
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(k):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms
+
+    for _ in range(max(args.warmup, 3)):
+        frame(True)
+        frame(False)
+    with ClockSampler(phys_gpu_index(local_rank)) as clk:
+        l0 = capi.lib.gs3d_launch_count()
+        ms = timed(lambda: frame(False), args.steps)
+        launches = capi.lib.gs3d_launch_count() - l0
+        ms_e2e = timed(lambda: frame(True), args.steps)
+    # single-GPU image of the same frame for the sharding check (bit-exact: tiles are independent)
+    full = frame(False)
+    with torch.no_grad():
+        ref_img = r(c2w_dev, cam)
+    shard_err = float((full - ref_img).abs().max())
+    n_dub = r.total_dub_gaussians
+    line = {
+        "metric": "forward FPS (6M Gaussians SH3 @3840x2160, tile rows sharded)", "value": 1000.0 * args.steps / ms,
+        "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+        "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": workload_desc(name, r.N, C, cam, 1), "n_dub": n_dub, "views_per_step": 1,
+                   "parallelism": f"tiles{world}" if world > 1 else "single"},
+        "impl_details": {"sharding": f"tile rows sharded over {world} rank(s), bands gathered on every rank",
+                         "l2_policy": "inputs larger than L2 (parameters 1.4 GB, duplicates 1 GB vs 126 MB L2)",
+                         "exact_decisions": not args.no_exact},
+        "sharded_vs_single_gpu_max_abs": shard_err,
+        "e2e": {"value": 1000.0 * args.steps / ms_e2e, "unit": "frames/s", "h2d_bytes_per_step": 48,
+                "d2h_bytes_per_step": int(cam.h * cam.w * 12)},
+        "gpu_launches": int(launches), "clocks": clk.summary(),
+    }
+    if args.check and world == 1:
+        line["parity"] = parity_block(name, args, torch)
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def parity_block(name, args, torch):
+    """--check: whole-path parity of the benchmarked workload against the reference GPU flow (test
+    infrastructure: oracle/fullsize_check.py + the real reference extension in oracle/_ref)."""
+    try:
+        from oracle import fullsize_check as F
+        from oracle import ref_gpu
+
+        ext = ref_gpu.load_reference_extension()
+        if ext is None:
+            return {"unavailable": "oracle/_ref/_gs_ref*.so absent"}
+        res = F.compare_whole_path(ext, "cfg2" if name == "cfg4" else name, N=args.n_gaussians, seed=0,
+                                   backward=name != "cfg5")
+        res["pass"] = F.passes(res)
+        return res
+    except Exception as e:
+        return {"error": str(e)}
+
+
+FFMA_PEAK_TFLOPS = 69.2  # profiles/r1_microbench_pipes.txt: FFMA loop on one B200 at 1965 MHz (no FP32 peak in MEASURED_PEAKS)
+
+
+def stage_rooflines(kernels_ms, N, C, cam, n_dub, views, staged, pairs, ncu_ok, touched_rows=0):
+    """One roofline object per stage (DESIGN.md 'Kernels' states the per-unit figures).
+
+    K1 / K2 / K4b are HBM-bound streaming kernels: achieved = algorithmic bytes / CUDA-event time against the
+    measured copy bandwidth.  K3 / K4a are bound by FP32 issue + shared memory, not by HBM: their entry is
+    bound = "issue", achieved = FLOP of the pairs actually evaluated / time against the measured FFMA rate; the
+    HBM figure (bytes per STAGED duplicate) is kept beside it.  `views` launches per step are summed in
+    kernels_ms, so per-launch quantities are multiplied by it."""
+    hbm_peak, peak_src = peaks()
+    CC = C * C
+    px = cam.w * cam.h
+    staged_fwd, staged_bwd = staged  # per step (all views of this rank)
+    pairs_fwd, pairs_bwd = pairs
+    per_dup = 4 + 48 + 12 * CC  # id + staging record + SH row
+    algo = {
+        # SURVEY 8d: read mean 12 + qvec 16 + svec 12 + alpha 4; write the 48-byte record + rect 16 + depth 4 + mask 1
+        "K1_project_cull": views * N * 89,  # (the kernel's own necessary traffic is 44 + 48 record + 21 = 113 B)
+        # own algorithm (DESIGN 'K2'): N-level depth passes + emit + tile passes + ranges
+        "K2_binning": views * N * (4 + 4 * 24 + 8) + n_dub * views * (8 + 2 * 24 + 4),
+        "K3_composite_fwd": staged_fwd * per_dup + views * px * 12,
+        "K4a_composite_bwd": staged_bwd * (per_dup + 4 * (7 + 3 * CC)) + views * px * 36,
+        # every row: mask + the three upstream gradients (29 B); rows with a gradient (the marked ones) also read the
+        # 44 B of parameters and read-modify-write 44 B of leaf gradients
+        "K4b_project_bwd": views * N * (28 + 1) + touched_rows * (44 + 2 * 44),
+    }
+    # FLOP of the compositing kernels (SURVEY 8d): 14 per tested pair; a contributing pair adds 6 C^2 + 12
+    # (forward) / recompute + gradient arithmetic + the 6 C^2 SH outer product (backward)
+    flops = {
+        "K3_composite_fwd": 256 * staged_fwd * 14 + pairs_fwd * (6 * CC + 12),
+        "K4a_composite_bwd": 256 * staged_bwd * 14 + pairs_bwd * (6 * CC + 12 + 6 * CC + 70),
+    }
+    ncu = {}
+    tfile = ROOT / "profiles" / "ncu_traffic.json"
+    if ncu_ok and tfile.exists():
+        try:
+            ncu = json.loads(tfile.read_text())
+        except Exception:
+            ncu = {}
+    out = {}
+    for k, ms in kernels_ms.items():
+        if k not in algo or ms <= 0:
+            continue
+        t = ncu.get(k) or {}
+        gbs = algo[k] / (ms * 1e-3) / 1e9
+        if k in flops:
+            tf = flops[k] / (ms * 1e-3) / 1e12
+            o = {"kernel": k, "bound": "issue", "achieved": tf, "peak": FFMA_PEAK_TFLOPS, "unit": "TFLOP/s",
+                 "frac": tf / FFMA_PEAK_TFLOPS, "peak_source": "measured FFMA loop (profiles/r1_microbench_pipes.txt)",
+                 "flop": flops[k], "pairs_tested": 256 * (staged_fwd if "fwd" in k else staged_bwd),
+                 "pairs_contributing": pairs_fwd if "fwd" in k else pairs_bwd,
+                 "hbm": {"achieved": gbs, "peak": hbm_peak, "unit": "GB/s", "frac": gbs / hbm_peak,
+                         "algorithmic_bytes": algo[k]},
+                 "staged_duplicates": staged_fwd if "fwd" in k else staged_bwd, "n_dub": n_dub}
+        else:
+            o = {"kernel": k, "bound": "hbm", "achieved": gbs, "peak": hbm_peak, "unit": "GB/s",
+                 "frac": gbs / hbm_peak, "peak_source": peak_src, "algorithmic_bytes": algo[k]}
+        o["launch_ms"] = ms / max(views, 1)
+        o["traffic"] = t.get("traffic")
+        o["traffic_source"] = t.get("source")
+        if t.get("traffic") and algo[k]:
+            o["traffic_over_algorithmic"] = t["traffic"] * views / algo[k]
+        util = {m: t[m] for m in ("issue_slot_pct", "fma_pipe_pct", "lsu_pipe_pct", "smem_wavefront_pct",
+                                  "warps_active_pct", "dram_pct") if t.get(m) is not None}
+        if util:
+            o["ncu_utilisation_pct_of_peak"] = util
+        out[k] = o
+    kk = {k: v for k, v in kernels_ms.items() if k in out}
+    dom = max(kk, key=kk.get) if kk else None
+    return out, dom
 
 
 # ---------------------------------------------------------------- reference arm
@@ -431,11 +667,13 @@ def run_reference(args, rank, local_rank, world):
     from gaussian_splatting_3d_b200 import synthetic as S
 
     name = args.workload
-    cam = S.make_camera(name)
+    cfg4, cfg5 = name == "cfg4", name == "cfg5"
+    scene = "cfg2" if cfg4 else name
+    cam = S.make_camera(scene)
     cpu = None
     if not args.no_cpu_baseline:
         try:
-            cpu = cpu_baseline(args, name)
+            cpu = cpu_baseline(args, scene)
         except Exception as e:
             cpu = {"error": str(e)}
     ext = None
@@ -465,21 +703,30 @@ def run_reference(args, rank, local_rank, world):
 
     dev = torch.device(f"cuda:{local_rank}")
     torch.cuda.set_device(dev)
-    sc = S.make_scene(name, seed=0, N=args.n_gaussians)
+    sc = S.make_scene(scene, seed=0, N=args.n_gaussians)
     C = sc["C"]
     ref = ref_gpu.ReferenceGPURenderer(ext, sc, dev, C)
-    c2w_host = sc["c2w"].pin_memory()
-    tgt_host = S.make_target(cam, 0).pin_memory()
-    c2w_dev, tgt_dev = c2w_host.to(dev), tgt_host.to(dev)
+    poses = S.ring_cameras(8) if cfg4 else [sc["c2w"]]  # cfg 4: the same 8 cameras per step, on one GPU
+    c2w_hosts = [c.pin_memory() for c in poses]
+    tgt_hosts = [S.make_target(cam, i).pin_memory() for i in range(len(poses))]
+    c2w_devs, tgt_devs = [c.to(dev) for c in c2w_hosts], [t.to(dev) for t in tgt_hosts]
+    c2w_host, tgt_host, c2w_dev = c2w_hosts[0], tgt_hosts[0], c2w_devs[0]
 
     def step(e2e):
-        c2w = c2w_host.to(dev, non_blocking=True) if e2e else c2w_dev
-        tgt = tgt_host.to(dev, non_blocking=True) if e2e else tgt_dev
+        if cfg5:  # a render: forward only, the frame is read back in the end-to-end form
+            with torch.no_grad():
+                out = ref.forward(c2w_host.to(dev, non_blocking=True) if e2e else c2w_dev, cam)
+            return out.cpu() if e2e else out
         ref.zero_grad()
-        out = ref.forward(c2w, cam)
-        loss = ((out - tgt) ** 2).mean()
-        loss.backward()
-        return float(loss.item()) if e2e else loss
+        total = None
+        for v in range(len(poses)):
+            c2w = c2w_hosts[v].to(dev, non_blocking=True) if e2e else c2w_devs[v]
+            tgt = tgt_hosts[v].to(dev, non_blocking=True) if e2e else tgt_devs[v]
+            out = ref.forward(c2w, cam)
+            loss = ((out - tgt) ** 2).mean()
+            loss.backward()  # autograd accumulates over the step's views
+            total = loss.detach() if total is None else total + loss.detach()
+        return float(total.item()) if e2e else total
 
     def fwd_only():
         with torch.no_grad():
@@ -514,14 +761,20 @@ def run_reference(args, rank, local_rank, world):
         os.dup2(saved_fd, 1)
         os.close(devnull)
         os.close(saved_fd)
+    nv = len(poses)
+    if cfg5:
+        base["metric"], base["unit"] = "forward FPS (6M Gaussians SH3 @3840x2160, tile rows sharded)", "frames/s"
+    base["scaling"] = "strong" if (cfg4 or cfg5) else "weak"
     base.update({
-        "value": 1000.0 * args.steps / ms, "ms_per_step": ms / args.steps,
+        "value": nv * 1000.0 * args.steps / ms, "ms_per_step": ms / args.steps,
         "fwd_fps": 1000.0 * args.steps / ms_fwd,
-        "config": {"workload": f"{name}: {ref.params['mean'].shape[0]} Gaussians, C={C}, {cam.w}x{cam.h}, reference "
-                               "CUDA extension (sm_100a build of /root/reference/gs/src, -DNDEBUG) behind the "
-                               "reference's torch-level flow", "n_dub": ref.total_dub_gaussians},
-        "e2e": {"value": 1000.0 * args.steps / ms_e2e, "unit": "iters/s",
-                "h2d_bytes_per_step": int(c2w_host.numel() * 4 + tgt_host.numel() * 4), "d2h_bytes_per_step": 4},
+        "config": {"workload": workload_desc(name, ref.params['mean'].shape[0], C, cam, nv),
+                   "n_dub": ref.total_dub_gaussians, "views_per_step": nv, "parallelism": "single"},
+        "impl_details": {"what": "reference CUDA extension (sm_100a build of /root/reference/gs/src, -DNDEBUG; its "
+                                 "device printf output discarded) behind the reference's torch-level flow, 1 GPU"},
+        "e2e": {"value": nv * 1000.0 * args.steps / ms_e2e, "unit": base["unit"],
+                "h2d_bytes_per_step": 48 if cfg5 else int(nv * (c2w_host.numel() * 4 + tgt_host.numel() * 4)),
+                "d2h_bytes_per_step": int(cam.h * cam.w * 12) if cfg5 else 4},
         "clocks": clk.summary(),
         "reference_kind": "gpu-extension",
     })

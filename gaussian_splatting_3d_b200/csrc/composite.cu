@@ -362,7 +362,7 @@ __device__ __forceinline__ void sh_colour(uint32_t h_addr, const Basis<CC> &Y, f
 #ifndef GS3D_FWD_MINB
 #define GS3D_FWD_MINB 4  // CTAs per SM the forward is compiled for (64 registers)
 #endif
-template <int C, int B, bool EXACT, bool RGB = false>
+template <int C, int B, bool EXACT, bool RGB = false, bool STATS = false>
 __global__ void __launch_bounds__(NTHREADS, GS3D_FWD_MINB)
 composite_fwd_kernel(const CompositeParams p) {
   constexpr int CC = C * C;
@@ -407,6 +407,7 @@ composite_fwd_kernel(const CompositeParams p) {
 
   float T = 1.0f, o0 = 0.0f, o1 = 0.0f, o2 = 0.0f;
   int last = 0;
+  [[maybe_unused]] unsigned int n_pairs = 0;  // STATS: contributing (pixel, Gaussian) pairs of this lane
   const float thresh = p.thresh;
   // the reference tests T (initially 1) before each Gaussian
   float dead = (inside && !(1.0f < thresh)) ? 0.0f : DEAD;
@@ -461,6 +462,7 @@ composite_fwd_kernel(const CompositeParams p) {
           o1 = fmaf(coeff, y[1], o1);
           o2 = fmaf(coeff, y[2], o2);
           T *= (1 - a * G);
+          if constexpr (STATS) ++n_pairs;
           last = cb * B + j + u + 1;
           // vol_render_sh.h:121-123 tests T before each Gaussian; T only changes here
           if (T < thresh) dead = DEAD;
@@ -471,6 +473,10 @@ composite_fwd_kernel(const CompositeParams p) {
   cp_async_wait<0>();
   // batches 0..cb have been staged when the loop ends at cb (all of them when it ran to completion)
   if (p.stats && threadIdx.x == 0) atomicAdd(p.stats, (unsigned long long)min(n_this, (cb + 1) * B));
+  if constexpr (STATS) {
+    const unsigned int wsum = __reduce_add_sync(0xffffffffu, n_pairs);
+    if (p.stats && lane == 0 && wsum) atomicAdd(p.stats + 2, (unsigned long long)wsum);
+  }
   if (!inside) return;
   if (p.bg && T > p.thresh) {  // vol_render_bg.h:90-94
     o0 = o0 * T + p.bg[0] * (1.0f - T);
@@ -488,308 +494,6 @@ composite_fwd_kernel(const CompositeParams p) {
 
 constexpr int WROW = 36;  // floats per row of the per-warp exchange tile (32 pixels + 4 pad: the
                           // scalar-sum LDS.128 of rows v and v+1 then fall on different banks)
-
-// Sum the 8 warp-private accumulator rows of one batch, reduce into global memory, re-zero.
-template <int CC, int B>
-__device__ __forceinline__ void flush_batch(const CompositeParams &p, float *s_acc, const int *s_ids_b, int nb) {
-  constexpr int SHF = 3 * CC;
-  constexpr int ROWP = (SHF + 6 + 3) & ~3;
-  constexpr int NQ = ROWP / 4;
-  for (int e = threadIdx.x; e < nb * NQ; e += NTHREADS) {
-    const int j = e / NQ, q = e - NQ * j;
-    float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-    for (int w = 0; w < NWARPS; ++w) {
-      float4 *a4 = reinterpret_cast<float4 *>(s_acc + (w * B + j) * ROWP) + q;
-      float4 v = *a4;
-      s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
-      *a4 = make_float4(0.f, 0.f, 0.f, 0.f);
-    }
-    if (s.x == 0.f && s.y == 0.f && s.z == 0.f && s.w == 0.f) continue;
-    const size_t g = (size_t)s_ids_b[j];
-    if (p.touched) p.touched[g] = 1;
-    const float sv4[4] = {s.x, s.y, s.z, s.w};
-    const int r0 = 4 * q;
-    if (CC % 4 == 0 && p.gsh_vec && r0 + 3 < SHF) {
-      const int c = r0 / CC, k = r0 - c * CC;
-      const size_t off = g * p.gsh_sg + c * p.gsh_sc + k;
-      if (p.g_sh_mc) {
-        multimem_red_add_v4(p.g_sh_mc + off, s);  // one instruction, the switch adds it on every GPU
-      } else if (p.n_peers > 0) {
-        for (int r = 0; r < p.n_peers; ++r) red_add_v4(p.g_sh_peer[r] + off, s);
-      } else {
-        red_add_v4(p.g_sh + off, s);
-      }
-    } else {
-#pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        const int r = r0 + u;
-        const float val = sv4[u];
-        if (val == 0.f) continue;
-        if (r < SHF) {
-          const int c = r / CC, k = r - c * CC;
-          const size_t off = g * p.gsh_sg + c * p.gsh_sc + k;
-          if (p.n_peers > 0) {
-            for (int q2 = 0; q2 < p.n_peers; ++q2) atomicAdd(p.g_sh_peer[q2] + off, val);
-          } else {
-            atomicAdd(p.g_sh + off, val);
-          }
-        } else {
-          const int v = r - SHF;
-          if (v == 0) atomicAdd(p.g_mean + 2 * g, val);
-          else if (v == 1) atomicAdd(p.g_mean + 2 * g + 1, val);
-          else if (v == 2) atomicAdd(p.g_cov + 4 * g, val);
-          else if (v == 3) { atomicAdd(p.g_cov + 4 * g + 1, val); atomicAdd(p.g_cov + 4 * g + 2, val); }
-          else if (v == 4) atomicAdd(p.g_cov + 4 * g + 3, val);
-          else if (v == 5) atomicAdd(p.g_alpha + g, val);
-        }
-      }
-    }
-  }
-}
-
-// Same id-ring pipeline as the forward.  The warp-private accumulators are double-buffered: the
-// flush of batch b-1 (sum over warps + global reductions) is issued right after the barrier that
-// starts batch b, so one barrier per batch orders staging, accumulation and flush.
-template <int C, int B, bool EXACT, bool RGB = false>
-__global__ void __launch_bounds__(NTHREADS, (B <= 16 ? 3 : 2))
-composite_bwd_kernel(const CompositeParams p) {
-  constexpr int CC = C * C;
-  constexpr int SHF = 3 * CC;
-  constexpr int ROW = SHF + 6;            // 3*CC SH sums, then gmx gmy g00 g01 g11 galpha
-  constexpr int ROWP = (ROW + 3) & ~3;    // padded to float4
-  constexpr int KL = CC < 16 ? CC : 16;   // lanes per half that own an SH column
-  constexpr int ACC = NWARPS * B * ROWP;  // floats per accumulator buffer
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  float4 *s_rec = reinterpret_cast<float4 *>(smem_raw);           // [2][B][3]
-  float *s_sh = reinterpret_cast<float *>(s_rec + 2 * B * 3);     // [2][B][SHF]
-  float *s_w = s_sh + 2 * B * SHF;                                // [NWARPS][9][WROW]
-  float *s_acc = s_w + NWARPS * 9 * WROW;                         // [2][NWARPS][B][ROWP]
-  int *s_ids = reinterpret_cast<int *>(s_acc + 2 * ACC);          // [4][B] (ring; the flush reads slot cb-1)
-
-  const int tile_id = blockIdx.x;
-  const int tile_y = tile_id / p.ntw, tile_x = tile_id - tile_y * p.ntw;
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int lx = 8 * (warp & 1) + (lane & 7), ly = 4 * (warp >> 1) + (lane >> 3);
-  const uint32_t gx = tile_x * TILE + lx, gy = tile_y * TILE + ly;
-  const bool inside = gx < p.W && gy < p.H;
-  const size_t pix = (size_t)gy * p.W + gx;
-
-  const int first = p.start[tile_id];
-  if (first == -1) return;
-  const int n_this = p.end[tile_id] - first;
-  if (n_this <= 0) return;
-
-  const float px = p.topleft[0] + gx * p.psx, py = p.topleft[1] + gy * p.psy;
-  Basis<CC> Y;
-  // Yt = Y_k(pixel 16*half + i), i = 0..15, for this lane's (k = lane & 15, half = lane >> 4):
-  // transposed through the (not yet used) accumulator area, kept as packed pairs.
-  const int kcol = lane & 15, half = lane >> 4;
-  f32x2 Yt[8];
-  {
-    float Yf[CC];
-    if constexpr (RGB) Yf[0] = 1.0f;  // colour gradient = plain sum of the per-pixel weights
-    else pixel_basis<C>(p.c2w, px, py, Yf);
-    Y.set(Yf);
-    constexpr int TS = CC + 1;            // [32][CC+1] per warp; 32*(CC+1) <= B*ROWP for B >= 16
-    float *tr = s_acc + warp * 32 * TS;
-#pragma unroll
-    for (int k = 0; k < CC; ++k) tr[lane * TS + k] = inside ? Yf[k] : 0.0f;
-    __syncwarp();
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const float lo = (kcol < CC) ? tr[(16 * half + 2 * i) * TS + kcol] : 0.0f;
-      const float hi = (kcol < CC) ? tr[(16 * half + 2 * i + 1) * TS + kcol] : 0.0f;
-      Yt[i] = pack2(lo, hi);
-    }
-  }
-  __syncthreads();
-  for (int e = threadIdx.x; e < 2 * ACC; e += NTHREADS) s_acc[e] = 0.0f;
-
-  // f* = colour still to come after the current Gaussian (the reference's `final - prefix`,
-  // vol_render_sh.h:336-342), kept as a running remainder instead of final and prefix separately
-  float g0 = 0.f, g1 = 0.f, g2 = 0.f, f0 = 0.f, f1 = 0.f, f2 = 0.f;
-  if (inside) {
-    g0 = p.grad_out[3 * pix + 0]; g1 = p.grad_out[3 * pix + 1]; g2 = p.grad_out[3 * pix + 2];
-    f0 = p.out_saved[3 * pix + 0]; f1 = p.out_saved[3 * pix + 1]; f2 = p.out_saved[3 * pix + 2];
-  }
-  float T = 1.0f;
-  const float thresh = p.thresh;
-  float dead = (inside && !(1.0f < thresh)) ? 0.0f : DEAD;
-  const int32_t *ids = p.ids + first;
-  const int n_batches = (n_this + B - 1) / B;
-  constexpr float INV_K = 1.0f / (-0.5f * 1.4426950408889634f);  // undo the conic pre-scale
-  const bool id_lane = threadIdx.x < B;
-
-  // per-lane shared addresses used by the warp reduction (computed once)
-  const uint32_t w_base = smem_u32(s_w + warp * 9 * WROW);
-  const uint32_t w_st = w_base + 4 * lane;                 // this lane's column in each of the 9 rows
-  const uint32_t w_sh = w_base + 4 * (16 * half);          // SH GEMV: 16 pixels of this lane's half
-  const int sv_row = lane >> 2, sv_q = lane & 3;           // scalar sums: row 3 + sv_row, quarter sv_q
-  const uint32_t w_sc = w_base + 4 * ((3 + (sv_row < 6 ? sv_row : 0)) * WROW + 8 * sv_q);
-  const uint32_t acc_warp = 4 * (warp * B * ROWP);
-
-  // prologue: ids of batch 0 -> ring slot 0, batch 0 in flight, ids of batch 1 -> ring slot 1
-  if (id_lane) s_ids[threadIdx.x] = threadIdx.x < n_this ? ids[threadIdx.x] : 0;
-  int my_id = (id_lane && B + threadIdx.x < n_this) ? ids[B + threadIdx.x] : 0;
-  __syncthreads();  // ids visible, accumulators zeroed
-  stage_batch<CC, B>(p, s_ids, min(B, n_this), s_rec, s_sh);
-  cp_async_commit();
-  if (id_lane) s_ids[B + threadIdx.x] = my_id;
-  my_id = (id_lane && 2 * B + threadIdx.x < n_this) ? ids[2 * B + threadIdx.x] : 0;
-
-  for (int cb = 0;; ++cb) {
-    cp_async_wait<0>();
-    // one barrier per batch: batch cb has landed, every warp is done with batch cb-1, ring slot
-    // published; the vote ends the tile when every pixel is saturated
-    const bool stop = __syncthreads_and(dead != 0.0f) || cb == n_batches;
-    const int buf = cb & 1;
-    if (!stop && cb + 1 < n_batches) {
-      const int nbuf = buf ^ 1;
-      stage_batch<CC, B>(p, s_ids + ((cb + 1) & 3) * B, min(B, n_this - (cb + 1) * B), s_rec + nbuf * B * 3,
-                         s_sh + nbuf * B * SHF);
-      cp_async_commit();
-    }
-    // flush of the previous batch (complete: every warp passed the barrier above after it)
-    if (cb > 0) flush_batch<CC, B>(p, s_acc + (buf ^ 1) * ACC, s_ids + ((cb - 1) & 3) * B, B);
-    if (stop) {  // batches 0..cb were staged (all of them when cb == n_batches)
-      if (p.stats && threadIdx.x == 0) atomicAdd(p.stats + 1, (unsigned long long)min(n_this, (cb + 1) * B));
-      break;
-    }
-    const int nb = min(B, n_this - cb * B);
-    {
-      uint32_t rec_a = smem_u32(s_rec + buf * B * 3);
-      uint32_t sh_a = smem_u32(s_sh + buf * B * SHF);
-      uint32_t row_a = smem_u32(s_acc + buf * ACC) + acc_warp;
-      for (int j = 0; j < nb; j += UB, rec_a += 48 * UB, sh_a += 4 * SHF * UB, row_a += 4 * ROWP * UB) {
-       if (!__any_sync(0xffffffffu, dead == 0.0f)) break;
-#pragma unroll
-       for (int uu = 0; uu < UB; ++uu) {
-        float w0 = 0.f, w1 = 0.f, w2 = 0.f, gmx = 0.f, gmy = 0.f, g00 = 0.f, g01 = 0.f, g11 = 0.f,
-              ga = 0.f;
-        bool contrib = false;
-        float pw, df;
-        const float4 r1 = lds128(rec_a + 48 * uu + 16);
-        const float4 r0 = pair_test(px, py, rec_a + 48 * uu, pw, df);
-        if (!(df - dead < -DECISION_MARGIN)) {
-          float G;
-          if (pair_decide<EXACT, RGB>(px, py, dead, pw, df, r0, rec_a + 48 * uu + 32, G)) {
-            contrib = true;
-            const float a = r0.z;
-            const float aG = a * G;
-            float coeff = (a * T) * G;
-            if (!RGB && isnan(coeff)) coeff = 0.0f;
-            float y[3];
-            sh_colour<CC, RGB>(sh_a + 4 * SHF * uu, Y, y);
-            f0 = fmaf(-coeff, y[0], f0);
-            f1 = fmaf(-coeff, y[1], f1);
-            f2 = fmaf(-coeff, y[2], f2);
-            if constexpr (RGB) {  // vol_render.h:305-307: grad_color += a T G * grad_out
-              w0 = coeff * g0; w1 = coeff * g1; w2 = coeff * g2;
-            } else {              // vol_render_sh.h:328-333
-              w0 = coeff * (y[0] * (1.0f - y[0])) * g0;
-              w1 = coeff * (y[1] * (1.0f - y[1])) * g1;
-              w2 = coeff * (y[2] * (1.0f - y[2])) * g2;
-            }
-            // vol_render_sh.h:336-342
-            const float one_m = 1.0f - aG;
-            const float inv1m = -rcp_approx(one_m);
-            float P = g0 * fmaf(y[0], T, f0 * inv1m);
-            P = fmaf(g1, fmaf(y[1], T, f1 * inv1m), P);
-            P = fmaf(g2, fmaf(y[2], T, f2 * inv1m), P);
-            // kernels.h:394-418 with the inverse covariance recovered from the conic
-            const float dx = px - r0.x, dy = py - r0.y;
-            const float i00 = r1.x * INV_K, i11 = r1.z * INV_K, i01 = (-0.5f * INV_K) * r1.y;
-            const float vx = fmaf(dx, i00, -dy * i01), vy = fmaf(dy, i11, -dx * i01);
-            const float gam = P * aG;
-            gmx = gam * vx;
-            gmy = gam * vy;
-            const float hg = 0.5f * gam;
-            g00 = hg * vx * vx;
-            g01 = hg * vx * vy;
-            g11 = hg * vy * vy;
-            ga = P * G;
-            T *= one_m;
-            if (T < thresh) dead = DEAD;  // vol_render_sh.h:296-298 (T only changes here)
-          }
-        }
-        if (__any_sync(0xffffffffu, contrib)) {
-        // ---- warp reduction over the 32 pixels through shared memory
-        sts32(w_st + 4 * 0 * WROW, w0);
-        sts32(w_st + 4 * 1 * WROW, w1);
-        sts32(w_st + 4 * 2 * WROW, w2);
-        sts32(w_st + 4 * 3 * WROW, gmx);
-        sts32(w_st + 4 * 4 * WROW, gmy);
-        sts32(w_st + 4 * 5 * WROW, g00);
-        sts32(w_st + 4 * 6 * WROW, g01);
-        sts32(w_st + 4 * 7 * WROW, g11);
-        sts32(w_st + 4 * 8 * WROW, ga);
-        __syncwarp();
-        f32x2 A0 = 0ull, A1 = 0ull, A2 = 0ull;
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          f32x2 lo, hi;
-          lds128_2(w_sh + 16 * q, lo, hi);
-          A0 = fma2(lo, Yt[2 * q], A0);
-          A0 = fma2(hi, Yt[2 * q + 1], A0);
-          lds128_2(w_sh + 4 * WROW + 16 * q, lo, hi);
-          A1 = fma2(lo, Yt[2 * q], A1);
-          A1 = fma2(hi, Yt[2 * q + 1], A1);
-          lds128_2(w_sh + 8 * WROW + 16 * q, lo, hi);
-          A2 = fma2(lo, Yt[2 * q], A2);
-          A2 = fma2(hi, Yt[2 * q + 1], A2);
-        }
-        float a0 = sum2(A0), a1 = sum2(A1), a2 = sum2(A2);
-        // six scalar sums: lane = 4*v + qd sums pixels 8*qd .. 8*qd+7 of row 3+v
-        float sv;
-        {
-          const float4 x0 = lds128(w_sc), x1 = lds128(w_sc + 16);
-          sv = ((x0.x + x0.y) + (x0.z + x0.w)) + ((x1.x + x1.y) + (x1.z + x1.w));
-        }
-        __syncwarp();
-        a0 += __shfl_xor_sync(0xffffffffu, a0, 16);
-        a1 += __shfl_xor_sync(0xffffffffu, a1, 16);
-        a2 += __shfl_xor_sync(0xffffffffu, a2, 16);
-        sv += __shfl_xor_sync(0xffffffffu, sv, 1);
-        sv += __shfl_xor_sync(0xffffffffu, sv, 2);
-        if (lane < KL) {
-          const uint32_t ra = row_a + 4 * ROWP * uu + 4 * lane;
-          sts32(ra, lds32(ra) + a0);
-          sts32(ra + 4 * CC, lds32(ra + 4 * CC) + a1);
-          sts32(ra + 8 * CC, lds32(ra + 8 * CC) + a2);
-        }
-        if (sv_q == 0 && sv_row < 6) {
-          const uint32_t ra = row_a + 4 * ROWP * uu + 4 * (SHF + sv_row);
-          sts32(ra, lds32(ra) + sv);
-        }
-        }
-       }
-      }
-    }
-    if (cb + 1 < n_batches) {
-      if (id_lane) s_ids[((cb + 2) & 3) * B + threadIdx.x] = my_id;
-      const int nxt = (cb + 3) * B + threadIdx.x;
-      my_id = (id_lane && nxt < n_this) ? ids[nxt] : 0;
-    }
-  }
-  cp_async_wait<0>();
-}
-
-
-// ---------------------------------------------------------------- backward, second generation
-//
-// Same arithmetic as composite_bwd_kernel, restructured after its ncu profile (profiles/r1_ncu_composite_v4):
-//  * warp-uniform control flow.  A warp executes the contributing path whenever ANY lane contributes, so the
-//    per-lane branches of the first version bought nothing and cost BSSY/BSYNC pairs plus branch-resolve stalls.
-//    Here every decision is a vote: lanes that do not contribute run the same straight-line code with G = 0
-//    (coeff, alpha*G and every partial gradient are then exactly 0, T is multiplied by exactly 1).
-//  * the warp-private accumulator row of a (warp, Gaussian) pair is written exactly once per batch: plain
-//    stores instead of read-modify-write (rows of pairs that did not contribute stay zero from the last flush).
-//  * NW warps per CTA (8 = a 16x16 tile, 4 = a 16x8 half tile: the batch barrier then waits for the slowest of
-//    4 warps instead of 8 and twice as many independent CTAs share an SM).
-//  * DIRECT: no CTA-level accumulators at all -- each warp reduces its own 3*C*C + 6 sums into global memory
-//    (red.global.add.v4.f32 from 14 lanes), which frees 57 KB of shared memory per CTA, allows batches of 64
-//    (one barrier per 64 Gaussians) and removes the flush pass, at 8x the global reductions.
 
 // One float4 (quad q of a Gaussian's [3*CC + 6]-float gradient row, padded to a multiple of 4) -> global memory.
 template <int CC>
@@ -834,75 +538,354 @@ __device__ __forceinline__ void emit_quad(const CompositeParams &p, size_t g, in
   }
 }
 
-// Sum the NW warp-private accumulator rows of one batch, reduce into global memory, re-zero.
-template <int CC, int B, int NW>
-__device__ __forceinline__ void flush_batch2(const CompositeParams &p, float *s_acc, const int *s_ids_b, int nb) {
-  constexpr int ROWP = (3 * CC + 6 + 3) & ~3;
-  constexpr int NQ = ROWP / 4;
-  for (int e = threadIdx.x; e < nb * NQ; e += NW * 32) {
-    const int j = e / NQ, q = e - NQ * j;
-    float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-    for (int w = 0; w < NW; ++w) {
-      float4 *a4 = reinterpret_cast<float4 *>(s_acc + (w * B + j) * ROWP) + q;
-      float4 v = *a4;
-      s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
-      *a4 = make_float4(0.f, 0.f, 0.f, 0.f);
-    }
-    if (s.x == 0.f && s.y == 0.f && s.z == 0.f && s.w == 0.f) continue;
-    const size_t g = (size_t)s_ids_b[j];
-    if (p.touched) p.touched[g] = 1;
-    emit_quad<CC>(p, g, q, s);
-  }
+// ---------------------------------------------------------------- backward kernel: mbarrier ring
+//
+// History (profiles/r2_bwd_variants.jsonl): the first version synchronised the CTA once per batch of 16 Gaussians and
+// branched per lane; ncu showed ~22 % of all warp samples waiting at that barrier.  Work per
+// (warp, Gaussian) is bimodal (~220 instructions when any of the warp's 32 pixels contributes, ~25 otherwise),
+// so at every batch of 16 the CTA waits for its unluckiest warp.  Here nothing is CTA-synchronous:
+//
+//   * a ring of RS stages of RG Gaussians; each stage holds the staged rows (record + SH) AND the warp-private
+//     accumulator rows of its Gaussians;
+//   * warp NW (the 9th) is producer and flusher: it stages a batch with cp.async.bulk (one 48-byte record copy
+//     and one SH-row copy per Gaussian, completion counted in bytes on the stage's `full` mbarrier), and when
+//     all NW pixel warps have arrived on the stage's `done` mbarrier it sums their accumulator rows, issues the
+//     global vector reductions and re-arms the stage with the batch RS stages ahead;
+//   * a pixel warp only ever waits for `full` of its next stage, i.e. it can run up to RS-1 stages ahead of the
+//     slowest warp of its tile; rows it did not write are skipped through a per-(stage, warp) bit mask, so
+//     nothing is zero-filled.
+// Early termination: every warp publishes "some pixel still alive" with its arrival; when no warp is alive the
+// producer arms the next stage as a sentinel (0 Gaussians) and the warps leave.
+
+#ifndef GS3D_MBAR_SUSPEND_NS
+#define GS3D_MBAR_SUSPEND_NS 20000u  // upper bound of one hardware suspend; an arrival wakes the warp earlier
+#endif
+constexpr int RS = 4;  // ring stages
+constexpr int RG = 8;  // Gaussians per stage
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("{\n.reg .b64 st;\nmbarrier.arrive.shared::cta.b64 st, [%0];\n}" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("{\n.reg .b64 st;\nmbarrier.arrive.expect_tx.shared::cta.b64 st, [%0], %1;\n}" ::"r"(bar), "r"(bytes)
+               : "memory");
+}
+// Blocking wait for the phase with the given parity.  try_wait carries a suspend-time hint, so a warp whose
+// data has not arrived is parked by the hardware instead of re-issuing the probe (without the hint the first
+// ring kernel spent 17 % of all issued instructions in this loop: profiles/r2_ncu_bwd_ring_v1.txt).
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n.reg .pred P1;\nLAB_WAIT:\nmbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1, %2;\n@P1 bra DONE;\n"
+      "bra LAB_WAIT;\nDONE:\n}" ::"r"(bar), "r"(parity), "r"(GS3D_MBAR_SUSPEND_NS)
+      : "memory");
+}
+// 1-D bulk copy global -> shared (TMA engine, UBLKCP); bytes is a multiple of 16, both addresses 16-byte aligned
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+               "l"(src), "r"(bytes), "r"(bar)
+               : "memory");
 }
 
-template <int C, int B, bool EXACT, bool RGB, int NW, bool DIRECT>
-__global__ void __launch_bounds__(NW * 32, (NW == 8 ? 3 : 6))
-composite_bwd2_kernel(const CompositeParams p) {
+// Per-lane state of the backward walk and one step of it (one Gaussian for the warp's 32 pixels).
+template <int C, bool EXACT, bool RGB, bool STATS = false>
+struct BwdWalk {
+  static constexpr int CC = C * C;
+  static constexpr int SHF = 3 * CC;
+  static constexpr int KL = CC < 16 ? CC : 16;
+  static constexpr uint32_t FULL = 0xffffffffu;
+  static constexpr float INV_K = 1.0f / (-0.5f * 1.4426950408889634f);  // undo the conic pre-scale
+  float px, py, g0, g1, g2, f0, f1, f2, T, dead, thresh;
+  Basis<CC> Y;
+  f32x2 Yt[8];
+  uint32_t w_st, w_sh, w_sc;
+  int lane, sv_row, sv_q;
+  unsigned int n_pairs;  // STATS: contributing (pixel, Gaussian) pairs of this lane
+
+  // rec / sh: shared addresses of the staged record and SH row; row: shared address of this warp's accumulator
+  // row for the Gaussian.  Returns (warp-uniform) whether the row was written.
+  __device__ __forceinline__ bool step(uint32_t rec, uint32_t sh, uint32_t row) {
+    float pw, df;
+    const float4 r1 = lds128(rec + 16);
+    const float4 r0 = pair_test(px, py, rec, pw, df);
+    const bool cand = !(df - dead < -DECISION_MARGIN) && dead == 0.0f;
+    bool contrib;
+    float G = ex2_approx(pw);
+    if constexpr (EXACT) {
+      contrib = cand && df >= DECISION_MARGIN && pw <= -1e-5f;  // far from the threshold: decided
+      const bool near_thr = cand && !contrib;                   // rare: the reference's arithmetic decides
+      if (__any_sync(FULL, near_thr)) {
+        if (near_thr) {
+          const float val = RGB ? gaussian_exact_f64(px - r0.x, py - r0.y, lds128(rec + 32))
+                                : gaussian_exact(px - r0.x, py - r0.y, lds128(rec + 32));
+          G = val;
+          contrib = !(r0.z * val < MIN_RENDER_ALPHA);
+        }
+      }
+    } else {
+      contrib = cand && df >= 0.0f && !(pw > 0.0f);
+    }
+    if (!__any_sync(FULL, contrib)) return false;
+    G = contrib ? G : 0.0f;
+    if constexpr (STATS) n_pairs += contrib ? 1u : 0u;
+    // ---- straight-line for the whole warp (G = 0 makes a lane's contribution exactly zero)
+    const float a = r0.z;
+    const float aG = a * G;
+    float coeff = (a * T) * G;
+    if (!RGB && isnan(coeff)) coeff = 0.0f;
+    float y[3];
+    sh_colour<CC, RGB>(sh, Y, y);
+    f0 = fmaf(-coeff, y[0], f0);
+    f1 = fmaf(-coeff, y[1], f1);
+    f2 = fmaf(-coeff, y[2], f2);
+    float w0, w1, w2;
+    if constexpr (RGB) {  // vol_render.h:305-307: grad_color += a T G * grad_out
+      w0 = coeff * g0; w1 = coeff * g1; w2 = coeff * g2;
+    } else {              // vol_render_sh.h:328-333
+      w0 = coeff * (y[0] * (1.0f - y[0])) * g0;
+      w1 = coeff * (y[1] * (1.0f - y[1])) * g1;
+      w2 = coeff * (y[2] * (1.0f - y[2])) * g2;
+    }
+    // vol_render_sh.h:336-342
+    const float one_m = 1.0f - aG;
+    const float inv1m = -rcp_approx(one_m);
+    float P = g0 * fmaf(y[0], T, f0 * inv1m);
+    P = fmaf(g1, fmaf(y[1], T, f1 * inv1m), P);
+    P = fmaf(g2, fmaf(y[2], T, f2 * inv1m), P);
+    // kernels.h:394-418 with the inverse covariance recovered from the conic
+    const float dx = px - r0.x, dy = py - r0.y;
+    const float i00 = r1.x * INV_K, i11 = r1.z * INV_K, i01 = (-0.5f * INV_K) * r1.y;
+    const float vx = fmaf(dx, i00, -dy * i01), vy = fmaf(dy, i11, -dx * i01);
+    const float gam = P * aG;
+    const float gmx = gam * vx, gmy = gam * vy;
+    const float hg = 0.5f * gam;
+    const float g00 = hg * vx * vx, g01 = hg * vx * vy, g11 = hg * vy * vy;
+    const float ga = P * G;
+    T *= one_m;
+    if (T < thresh) dead = DEAD;  // vol_render_sh.h:296-298 (T only changes here)
+    // ---- warp reduction over the 32 pixels through shared memory
+    sts32(w_st + 4 * 0 * WROW, w0);
+    sts32(w_st + 4 * 1 * WROW, w1);
+    sts32(w_st + 4 * 2 * WROW, w2);
+    sts32(w_st + 4 * 3 * WROW, gmx);
+    sts32(w_st + 4 * 4 * WROW, gmy);
+    sts32(w_st + 4 * 5 * WROW, g00);
+    sts32(w_st + 4 * 6 * WROW, g01);
+    sts32(w_st + 4 * 7 * WROW, g11);
+    sts32(w_st + 4 * 8 * WROW, ga);
+    __syncwarp();
+    f32x2 A0 = 0ull, A1 = 0ull, A2 = 0ull;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      f32x2 lo, hi;
+      lds128_2(w_sh + 16 * q, lo, hi);
+      A0 = fma2(lo, Yt[2 * q], A0);
+      A0 = fma2(hi, Yt[2 * q + 1], A0);
+      lds128_2(w_sh + 4 * WROW + 16 * q, lo, hi);
+      A1 = fma2(lo, Yt[2 * q], A1);
+      A1 = fma2(hi, Yt[2 * q + 1], A1);
+      lds128_2(w_sh + 8 * WROW + 16 * q, lo, hi);
+      A2 = fma2(lo, Yt[2 * q], A2);
+      A2 = fma2(hi, Yt[2 * q + 1], A2);
+    }
+    float a0 = sum2(A0), a1 = sum2(A1), a2 = sum2(A2);
+    // six scalar sums: lane = 4*v + qd sums pixels 8*qd .. 8*qd+7 of row 3+v
+    float sv;
+    {
+      const float4 x0 = lds128(w_sc), x1 = lds128(w_sc + 16);
+      sv = ((x0.x + x0.y) + (x0.z + x0.w)) + ((x1.x + x1.y) + (x1.z + x1.w));
+    }
+    __syncwarp();
+    a0 += __shfl_xor_sync(FULL, a0, 16);
+    a1 += __shfl_xor_sync(FULL, a1, 16);
+    a2 += __shfl_xor_sync(FULL, a2, 16);
+    sv += __shfl_xor_sync(FULL, sv, 1);
+    sv += __shfl_xor_sync(FULL, sv, 2);
+    if (lane < KL) {  // a (warp, Gaussian) row is written at most once per use of its stage: plain stores
+      sts32(row + 4 * lane, a0);
+      sts32(row + 4 * (CC + lane), a1);
+      sts32(row + 4 * (2 * CC + lane), a2);
+    }
+    if (sv_q == 0 && sv_row < 6) sts32(row + 4 * (SHF + sv_row), sv);
+    return true;
+  }
+};
+
+template <int C, bool EXACT, bool RGB, bool STATS>
+__global__ void __launch_bounds__(NTHREADS + 32, 3)
+composite_bwd3_kernel(const CompositeParams p) {
   constexpr int CC = C * C;
   constexpr int SHF = 3 * CC;
-  constexpr int ROW = SHF + 6;            // 3*CC SH sums, then gmx gmy g00 g01 g11 galpha
-  constexpr int ROWP = (ROW + 3) & ~3;    // padded to float4
+  constexpr int ROW = SHF + 6;
+  constexpr int ROWP = (ROW + 3) & ~3;
   constexpr int NQ = ROWP / 4;
-  constexpr int KL = CC < 16 ? CC : 16;   // lanes per half that own an SH column
-  constexpr int NT = NW * 32;
-  constexpr int SUBS = 8 / NW;            // CTAs per 16x16 tile
-  constexpr int ACC = NW * B * ROWP;      // floats per accumulator buffer (!DIRECT)
+  constexpr int NW = NWARPS;
   constexpr uint32_t FULL = 0xffffffffu;
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  float4 *s_rec = reinterpret_cast<float4 *>(smem_raw);           // [2][B][3]
-  float *s_sh = reinterpret_cast<float *>(s_rec + 2 * B * 3);     // [2][B][SHF]
-  float *s_w = s_sh + 2 * B * SHF;                                // [NW][9][WROW]
-  float *s_acc = s_w + NW * 9 * WROW;                             // DIRECT ? [NW][ROWP] : [2][NW][B][ROWP]
-  int *s_ids = reinterpret_cast<int *>(s_acc + (DIRECT ? NW * ROWP : 2 * ACC));  // [4][B] ring
+  float4 *s_rec = reinterpret_cast<float4 *>(smem_raw);            // [RS][RG][3]
+  float *s_sh = reinterpret_cast<float *>(s_rec + RS * RG * 3);    // [RS][RG][SHF]  (SHF*4 bytes per row)
+  float *s_w = s_sh + RS * RG * SHF;                               // [NW][9][WROW]
+  float *s_acc = s_w + NW * 9 * WROW;                              // [RS][NW][RG][ROWP]
+  int *s_idr = reinterpret_cast<int *>(s_acc + RS * NW * RG * ROWP);  // [2*RS][RG] id ring
+  int *s_nvalid = s_idr + 2 * RS * RG;                             // [RS]
+  unsigned char *s_mask = reinterpret_cast<unsigned char *>(s_nvalid + RS);  // [RS][NW] rows written
+  unsigned char *s_alive = s_mask + RS * NW;                       // [RS][NW]
+  unsigned long long *s_bar = reinterpret_cast<unsigned long long *>(s_alive + RS * NW);  // full[RS], done[RS]
+  static_assert((RS * NW) % 4 == 0 && NW == 8, "mask rows are read as 64-bit words");
 
-  const int tile_id = blockIdx.x / SUBS, sub = blockIdx.x - tile_id * SUBS;
+  const int tile_id = blockIdx.x;
   const int tile_y = tile_id / p.ntw, tile_x = tile_id - tile_y * p.ntw;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int lx = 8 * (warp & 1) + (lane & 7), ly = 4 * (warp >> 1) + (lane >> 3) + sub * (2 * NW);
-  const uint32_t gx = tile_x * TILE + lx, gy = tile_y * TILE + ly;
-  const bool inside = gx < p.W && gy < p.H;
-  const size_t pix = (size_t)gy * p.W + gx;
-
   const int first = p.start[tile_id];
   if (first == -1) return;
   const int n_this = p.end[tile_id] - first;
   if (n_this <= 0) return;
+  const int32_t *ids = p.ids + first;
+  const int n_batches = (n_this + RG - 1) / RG;
+  const uint32_t bar_full = smem_u32(s_bar), bar_done = smem_u32(s_bar + RS);
 
-  const float px = p.topleft[0] + gx * p.psx, py = p.topleft[1] + gy * p.psy;
-  Basis<CC> Y;
-  // Yt = Y_k(pixel 16*half + i), i = 0..15, for this lane's (k = lane & 15, half = lane >> 4): transposed
-  // through the warp's (not yet used) exchange tile, eight basis functions per round, kept as packed pairs.
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int s2 = 0; s2 < RS; ++s2) {
+      mbar_init(bar_full + 8 * s2, 1);
+      mbar_init(bar_done + 8 * s2, NW);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (threadIdx.x < RS * RG) s_idr[threadIdx.x] = threadIdx.x < n_this ? ids[threadIdx.x] : 0;
+  __syncthreads();
+
+  if (warp == NW) {
+    // ================================================================= producer / flusher warp
+    unsigned long long staged = 0;
+    int end_b = n_batches;  // first batch index armed as the sentinel
+    auto arm = [&](int t) {
+      const int s2 = t & (RS - 1);
+      if (t > end_b) return;
+      if (t == end_b) {  // sentinel: no Gaussians
+        if (lane == 0) {
+          s_nvalid[s2] = 0;
+          mbar_arrive(bar_full + 8 * s2);
+        }
+        return;
+      }
+      asm volatile("cp.async.wait_all;" ::: "memory");  // this warp's own id prefetches have landed
+      __syncwarp();
+      const int nv = min(RG, n_this - RG * t);
+      const int *idp = s_idr + (t & (2 * RS - 1)) * RG;
+      // ids of batch t + RS -> the ring slot batch t - RS used (its flush is done)
+      {
+        const int nxt = RG * (t + RS) + lane;
+        if (lane < RG) {
+          int *dst = s_idr + ((t + RS) & (2 * RS - 1)) * RG + lane;
+          if (nxt < n_this) cp_async_4(dst, ids + nxt);
+          else *dst = 0;
+        }
+      }
+      // null records behind the batch (the walk is unrolled by UB): threshold +inf never contributes
+      if (lane < (RG - nv) * 3) {
+        const int e = nv * 3 + lane;
+        s_rec[s2 * RG * 3 + e] = (e % 3 == 0) ? make_float4(0.f, 0.f, 0.f, __int_as_float(0x7f800000))
+                                              : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+      const bool bulk = RGB ? false : (p.sh_vec != 0);
+      if (bulk) {
+        const bool dense = p.sh_sc == (uint32_t)CC;
+        const uint32_t sh_bytes = 4 * SHF;
+        __syncwarp();  // the padding stores above are ordered before lane 0's (releasing) arrival
+        if (lane == 0) {
+          s_nvalid[s2] = nv;
+          mbar_arrive_expect_tx(bar_full + 8 * s2, (uint32_t)nv * (48 + sh_bytes));
+        }
+        __syncwarp();
+        if (lane < nv) {
+          const size_t g = (size_t)idp[lane];
+          bulk_g2s(smem_u32(s_rec + (s2 * RG + lane) * 3), p.records + 3 * g, 48, bar_full + 8 * s2);
+          const uint32_t dst = smem_u32(s_sh + (s2 * RG + lane) * SHF);
+          if (dense) {
+            bulk_g2s(dst, p.sh + g * p.sh_sg, sh_bytes, bar_full + 8 * s2);
+          } else {
+#pragma unroll
+            for (int c = 0; c < 3; ++c)
+              bulk_g2s(dst + 4 * c * CC, p.sh + g * p.sh_sg + c * p.sh_sc, 4 * CC, bar_full + 8 * s2);
+          }
+        }
+      } else {
+        // element-wise staging (SH rows that are not 16-byte addressable, RGB colours): this warp can afford to
+        // wait for its copies -- nobody waits for IT unless the whole ring has run dry
+        for (int e = lane; e < nv * 3; e += 32)
+          cp_async_16(s_rec + s2 * RG * 3 + e, p.records + 3 * (size_t)idp[e / 3] + (e % 3));
+        for (int e = lane; e < nv * SHF; e += 32) {
+          const int j = e / SHF, r = e - SHF * j;
+          const int c = r / CC, k = r - c * CC;
+          cp_async_4(s_sh + (s2 * RG + j) * SHF + r, p.sh + (size_t)idp[j] * p.sh_sg + c * p.sh_sc + k);
+        }
+        asm volatile("cp.async.wait_all;" ::: "memory");
+        __threadfence_block();
+        __syncwarp();
+        if (lane == 0) {
+          s_nvalid[s2] = nv;
+          mbar_arrive(bar_full + 8 * s2);
+        }
+      }
+      staged += (unsigned long long)nv;
+    };
+    for (int t = 0; t < RS; ++t) arm(t);
+    for (int b = 0; b < end_b; ++b) {
+      const int s2 = b & (RS - 1);
+      mbar_wait(bar_done + 8 * s2, (b / RS) & 1);
+      const unsigned long long masks = *reinterpret_cast<const unsigned long long *>(s_mask + s2 * NW);
+      const unsigned long long alive = *reinterpret_cast<const unsigned long long *>(s_alive + s2 * NW);
+      if (alive == 0ull) end_b = min(end_b, b + RS);
+      if (masks != 0ull) {
+        const int nv = min(RG, n_this - RG * b);
+        const int *idp = s_idr + (b & (2 * RS - 1)) * RG;
+        const float *acc = s_acc + s2 * NW * RG * ROWP;
+        for (int e = lane; e < nv * NQ; e += 32) {
+          const int j = e / NQ, q = e - NQ * j;
+          float4 sum = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+          for (int w = 0; w < NW; ++w) {
+            if ((masks >> (8 * w + j)) & 1ull) {
+              const float4 v = *(reinterpret_cast<const float4 *>(acc + (w * RG + j) * ROWP) + q);
+              sum.x += v.x; sum.y += v.y; sum.z += v.z; sum.w += v.w;
+            }
+          }
+          if (sum.x == 0.f && sum.y == 0.f && sum.z == 0.f && sum.w == 0.f) continue;
+          const size_t g = (size_t)idp[j];
+          if (p.touched) p.touched[g] = 1;
+          emit_quad<CC>(p, g, q, sum);
+        }
+      }
+      __syncwarp();
+      arm(b + RS);
+    }
+    asm volatile("cp.async.wait_all;" ::: "memory");
+    if (p.stats && lane == 0) atomicAdd(p.stats + 1, staged);
+    return;
+  }
+
+  // ===================================================================== pixel warps
+  const int lx = 8 * (warp & 1) + (lane & 7), ly = 4 * (warp >> 1) + (lane >> 3);
+  const uint32_t gx = tile_x * TILE + lx, gy = tile_y * TILE + ly;
+  const bool inside = gx < p.W && gy < p.H;
+  const size_t pix = (size_t)gy * p.W + gx;
+  BwdWalk<C, EXACT, RGB, STATS> wk;
+  wk.n_pairs = 0;
+  wk.px = p.topleft[0] + gx * p.psx;
+  wk.py = p.topleft[1] + gy * p.psy;
+  wk.lane = lane;
   const int kcol = lane & 15, half = lane >> 4;
-  f32x2 Yt[8];
   {
     float Yf[CC];
     if constexpr (RGB) Yf[0] = 1.0f;  // colour gradient = plain sum of the per-pixel weights
-    else pixel_basis<C>(p.c2w, px, py, Yf);
-    Y.set(Yf);
+    else pixel_basis<C>(p.c2w, wk.px, wk.py, Yf);
+    wk.Y.set(Yf);
     float *tr = s_w + warp * 9 * WROW;  // [32][9] floats (288 <= 9 * WROW)
 #pragma unroll
-    for (int i = 0; i < 8; ++i) Yt[i] = 0ull;
+    for (int i = 0; i < 8; ++i) wk.Yt[i] = 0ull;
 #pragma unroll
     for (int rd = 0; rd < (CC + 7) / 8; ++rd) {
 #pragma unroll
@@ -912,204 +895,58 @@ composite_bwd2_kernel(const CompositeParams p) {
       if ((kcol >> 3) == rd && kcol < CC) {
 #pragma unroll
         for (int i = 0; i < 8; ++i)
-          Yt[i] = pack2(tr[(16 * half + 2 * i) * 9 + (kcol & 7)], tr[(16 * half + 2 * i + 1) * 9 + (kcol & 7)]);
+          wk.Yt[i] = pack2(tr[(16 * half + 2 * i) * 9 + (kcol & 7)], tr[(16 * half + 2 * i + 1) * 9 + (kcol & 7)]);
       }
       __syncwarp();
     }
   }
-  if constexpr (!DIRECT) {
-    for (int e = threadIdx.x; e < 2 * ACC; e += NT) s_acc[e] = 0.0f;
-  }
-
-  // f* = colour still to come after the current Gaussian (the reference's `final - prefix`,
-  // vol_render_sh.h:336-342), kept as a running remainder instead of final and prefix separately
-  float g0 = 0.f, g1 = 0.f, g2 = 0.f, f0 = 0.f, f1 = 0.f, f2 = 0.f;
+  wk.g0 = wk.g1 = wk.g2 = wk.f0 = wk.f1 = wk.f2 = 0.f;
   if (inside) {
-    g0 = p.grad_out[3 * pix + 0]; g1 = p.grad_out[3 * pix + 1]; g2 = p.grad_out[3 * pix + 2];
-    f0 = p.out_saved[3 * pix + 0]; f1 = p.out_saved[3 * pix + 1]; f2 = p.out_saved[3 * pix + 2];
+    wk.g0 = p.grad_out[3 * pix + 0]; wk.g1 = p.grad_out[3 * pix + 1]; wk.g2 = p.grad_out[3 * pix + 2];
+    wk.f0 = p.out_saved[3 * pix + 0]; wk.f1 = p.out_saved[3 * pix + 1]; wk.f2 = p.out_saved[3 * pix + 2];
   }
-  float T = 1.0f;
-  const float thresh = p.thresh;
-  float dead = (inside && !(1.0f < thresh)) ? 0.0f : DEAD;
-  const int32_t *ids = p.ids + first;
-  const int n_batches = (n_this + B - 1) / B;
-  constexpr float INV_K = 1.0f / (-0.5f * 1.4426950408889634f);  // undo the conic pre-scale
-  const bool id_lane = threadIdx.x < B;
-  static_assert(B <= NW * 32, "one thread per id of a batch");
-
-  // per-lane shared addresses used by the warp reduction (computed once)
-  const uint32_t w_base = smem_u32(s_w + warp * 9 * WROW);
-  const uint32_t w_st = w_base + 4 * lane;                 // this lane's column in each of the 9 rows
-  const uint32_t w_sh = w_base + 4 * (16 * half);          // SH GEMV: 16 pixels of this lane's half
-  const int sv_row = lane >> 2, sv_q = lane & 3;           // scalar sums: row 3 + sv_row, quarter sv_q
-  const uint32_t w_sc = w_base + 4 * ((3 + (sv_row < 6 ? sv_row : 0)) * WROW + 8 * sv_q);
-  const uint32_t acc_warp = DIRECT ? 4 * (warp * ROWP) : 4 * (warp * B * ROWP);
-
-  // prologue: ids of batch 0 -> ring slot 0, batch 0 in flight, ids of batch 1 -> ring slot 1
-  if (id_lane) s_ids[threadIdx.x] = threadIdx.x < n_this ? ids[threadIdx.x] : 0;
-  int my_id = (id_lane && B + threadIdx.x < n_this) ? ids[B + threadIdx.x] : 0;
-  __syncthreads();  // ids visible, accumulators zeroed, basis transposition done
-  stage_batch<CC, B, NT>(p, s_ids, min(B, n_this), s_rec, s_sh);
-  cp_async_commit();
-  if (id_lane) s_ids[B + threadIdx.x] = my_id;
-  my_id = (id_lane && 2 * B + threadIdx.x < n_this) ? ids[2 * B + threadIdx.x] : 0;
-
-  for (int cb = 0;; ++cb) {
-    cp_async_wait<0>();
-    // one barrier per batch: batch cb has landed, every warp is done with batch cb-1, ring slot
-    // published; the vote ends the tile when every pixel is saturated
-    const bool stop = __syncthreads_and(dead != 0.0f) || cb == n_batches;
-    const int buf = cb & 1;
-    if (!stop && cb + 1 < n_batches) {
-      const int nbuf = buf ^ 1;
-      stage_batch<CC, B, NT>(p, s_ids + ((cb + 1) & 3) * B, min(B, n_this - (cb + 1) * B), s_rec + nbuf * B * 3,
-                             s_sh + nbuf * B * SHF);
-      cp_async_commit();
-    }
-    // flush of the previous batch (complete: every warp passed the barrier above after it)
-    if constexpr (!DIRECT) {
-      if (cb > 0) flush_batch2<CC, B, NW>(p, s_acc + (buf ^ 1) * ACC, s_ids + ((cb - 1) & 3) * B, B);
-    }
-    if (stop) {  // batches 0..cb were staged (all of them when cb == n_batches)
-      if (p.stats && threadIdx.x == 0 && sub == 0)
-        atomicAdd(p.stats + 1, (unsigned long long)min(n_this, (cb + 1) * B));
-      break;
-    }
-    const int nb = min(B, n_this - cb * B);
-    {
-      uint32_t rec_a = smem_u32(s_rec + buf * B * 3);
-      uint32_t sh_a = smem_u32(s_sh + buf * B * SHF);
-      uint32_t row_a = smem_u32(s_acc + (DIRECT ? 0 : buf * ACC)) + acc_warp;
-      const int *ids_b = s_ids + (cb & 3) * B;
-      for (int j = 0; j < nb; j += UB, rec_a += 48 * UB, sh_a += 4 * SHF * UB, row_a += DIRECT ? 0 : 4 * ROWP * UB) {
-       if (!__any_sync(FULL, dead == 0.0f)) break;
-#pragma unroll
-       for (int uu = 0; uu < UB; ++uu) {
-        float pw, df;
-        const float4 r1 = lds128(rec_a + 48 * uu + 16);
-        const float4 r0 = pair_test(px, py, rec_a + 48 * uu, pw, df);
-        // ---- decisions, as votes.  `dead` is 0 for a live pixel and 1e30 for a finished one.
-        const bool cand = !(df - dead < -DECISION_MARGIN) && dead == 0.0f;
-        bool contrib;
-        float G = ex2_approx(pw);
-        if constexpr (EXACT) {
-          contrib = cand && df >= DECISION_MARGIN && pw <= -1e-5f;  // far from the threshold: decided
-          const bool near_thr = cand && !contrib;                   // rare: the reference's arithmetic decides
-          if (__any_sync(FULL, near_thr)) {
-            if (near_thr) {
-              const float val = RGB ? gaussian_exact_f64(px - r0.x, py - r0.y, lds128(rec_a + 48 * uu + 32))
-                                    : gaussian_exact(px - r0.x, py - r0.y, lds128(rec_a + 48 * uu + 32));
-              G = val;
-              contrib = !(r0.z * val < MIN_RENDER_ALPHA);
-            }
-          }
-        } else {
-          contrib = cand && df >= 0.0f && !(pw > 0.0f);
-        }
-        if (!__any_sync(FULL, contrib)) continue;
-        G = contrib ? G : 0.0f;
-        // ---- straight-line for the whole warp (G = 0 makes a lane's contribution exactly zero)
-        const float a = r0.z;
-        const float aG = a * G;
-        float coeff = (a * T) * G;
-        if (!RGB && isnan(coeff)) coeff = 0.0f;
-        float y[3];
-        sh_colour<CC, RGB>(sh_a + 4 * SHF * uu, Y, y);
-        f0 = fmaf(-coeff, y[0], f0);
-        f1 = fmaf(-coeff, y[1], f1);
-        f2 = fmaf(-coeff, y[2], f2);
-        float w0, w1, w2;
-        if constexpr (RGB) {  // vol_render.h:305-307: grad_color += a T G * grad_out
-          w0 = coeff * g0; w1 = coeff * g1; w2 = coeff * g2;
-        } else {              // vol_render_sh.h:328-333
-          w0 = coeff * (y[0] * (1.0f - y[0])) * g0;
-          w1 = coeff * (y[1] * (1.0f - y[1])) * g1;
-          w2 = coeff * (y[2] * (1.0f - y[2])) * g2;
-        }
-        // vol_render_sh.h:336-342
-        const float one_m = 1.0f - aG;
-        const float inv1m = -rcp_approx(one_m);
-        float P = g0 * fmaf(y[0], T, f0 * inv1m);
-        P = fmaf(g1, fmaf(y[1], T, f1 * inv1m), P);
-        P = fmaf(g2, fmaf(y[2], T, f2 * inv1m), P);
-        // kernels.h:394-418 with the inverse covariance recovered from the conic
-        const float dx = px - r0.x, dy = py - r0.y;
-        const float i00 = r1.x * INV_K, i11 = r1.z * INV_K, i01 = (-0.5f * INV_K) * r1.y;
-        const float vx = fmaf(dx, i00, -dy * i01), vy = fmaf(dy, i11, -dx * i01);
-        const float gam = P * aG;
-        const float gmx = gam * vx, gmy = gam * vy;
-        const float hg = 0.5f * gam;
-        const float g00 = hg * vx * vx, g01 = hg * vx * vy, g11 = hg * vy * vy;
-        const float ga = P * G;
-        T *= one_m;
-        if (T < thresh) dead = DEAD;  // vol_render_sh.h:296-298 (T only changes here)
-        // ---- warp reduction over the 32 pixels through shared memory
-        sts32(w_st + 4 * 0 * WROW, w0);
-        sts32(w_st + 4 * 1 * WROW, w1);
-        sts32(w_st + 4 * 2 * WROW, w2);
-        sts32(w_st + 4 * 3 * WROW, gmx);
-        sts32(w_st + 4 * 4 * WROW, gmy);
-        sts32(w_st + 4 * 5 * WROW, g00);
-        sts32(w_st + 4 * 6 * WROW, g01);
-        sts32(w_st + 4 * 7 * WROW, g11);
-        sts32(w_st + 4 * 8 * WROW, ga);
-        __syncwarp();
-        f32x2 A0 = 0ull, A1 = 0ull, A2 = 0ull;
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          f32x2 lo, hi;
-          lds128_2(w_sh + 16 * q, lo, hi);
-          A0 = fma2(lo, Yt[2 * q], A0);
-          A0 = fma2(hi, Yt[2 * q + 1], A0);
-          lds128_2(w_sh + 4 * WROW + 16 * q, lo, hi);
-          A1 = fma2(lo, Yt[2 * q], A1);
-          A1 = fma2(hi, Yt[2 * q + 1], A1);
-          lds128_2(w_sh + 8 * WROW + 16 * q, lo, hi);
-          A2 = fma2(lo, Yt[2 * q], A2);
-          A2 = fma2(hi, Yt[2 * q + 1], A2);
-        }
-        float a0 = sum2(A0), a1 = sum2(A1), a2 = sum2(A2);
-        // six scalar sums: lane = 4*v + qd sums pixels 8*qd .. 8*qd+7 of row 3+v
-        float sv;
-        {
-          const float4 x0 = lds128(w_sc), x1 = lds128(w_sc + 16);
-          sv = ((x0.x + x0.y) + (x0.z + x0.w)) + ((x1.x + x1.y) + (x1.z + x1.w));
-        }
-        __syncwarp();
-        a0 += __shfl_xor_sync(FULL, a0, 16);
-        a1 += __shfl_xor_sync(FULL, a1, 16);
-        a2 += __shfl_xor_sync(FULL, a2, 16);
-        sv += __shfl_xor_sync(FULL, sv, 1);
-        sv += __shfl_xor_sync(FULL, sv, 2);
-        const uint32_t ra = row_a + (DIRECT ? 0 : 4 * ROWP * uu);
-        if (lane < KL) {  // this (warp, Gaussian) row is written once per batch: plain stores
-          sts32(ra + 4 * lane, a0);
-          sts32(ra + 4 * (CC + lane), a1);
-          sts32(ra + 4 * (2 * CC + lane), a2);
-        }
-        if (sv_q == 0 && sv_row < 6) sts32(ra + 4 * (SHF + sv_row), sv);
-        if constexpr (DIRECT) {
-          __syncwarp();
-          if (lane < NQ) {
-            const float4 q4 = lds128(ra + 16 * lane);
-            if (!(q4.x == 0.f && q4.y == 0.f && q4.z == 0.f && q4.w == 0.f)) {
-              const size_t g = (size_t)ids_b[j + uu];
-              if (lane == 0 && p.touched) p.touched[g] = 1;
-              emit_quad<CC>(p, g, lane, q4);
-            }
-          }
-          __syncwarp();
-        }
-       }
-      }
-    }
-    if (cb + 1 < n_batches) {
-      if (id_lane) s_ids[((cb + 2) & 3) * B + threadIdx.x] = my_id;
-      const int nxt = (cb + 3) * B + threadIdx.x;
-      my_id = (id_lane && nxt < n_this) ? ids[nxt] : 0;
-    }
+  wk.T = 1.0f;
+  wk.thresh = p.thresh;
+  wk.dead = (inside && !(1.0f < p.thresh)) ? 0.0f : DEAD;
+  {
+    const uint32_t w_base = smem_u32(s_w + warp * 9 * WROW);
+    wk.w_st = w_base + 4 * lane;
+    wk.w_sh = w_base + 4 * (16 * half);
+    wk.sv_row = lane >> 2;
+    wk.sv_q = lane & 3;
+    wk.w_sc = w_base + 4 * ((3 + (wk.sv_row < 6 ? wk.sv_row : 0)) * WROW + 8 * wk.sv_q);
   }
-  cp_async_wait<0>();
+  const uint32_t rec0 = smem_u32(s_rec), sh0 = smem_u32(s_sh);
+  const uint32_t acc0 = smem_u32(s_acc) + 4 * (warp * RG * ROWP);
+
+  for (int b = 0;; ++b) {
+    const int s2 = b & (RS - 1);
+    mbar_wait(bar_full + 8 * s2, (b / RS) & 1);
+    const int nv = s_nvalid[s2];
+    if (nv == 0) break;
+    uint32_t rec_a = rec0 + 48 * (s2 * RG);
+    uint32_t sh_a = sh0 + 4 * SHF * (s2 * RG);
+    uint32_t row_a = acc0 + 4 * (s2 * NW * RG * ROWP);
+    uint32_t mask = 0;
+    for (int j = 0; j < nv; j += UB, rec_a += 48 * UB, sh_a += 4 * SHF * UB, row_a += 4 * ROWP * UB) {
+      if (!__any_sync(FULL, wk.dead == 0.0f)) break;
+#pragma unroll
+      for (int uu = 0; uu < UB; ++uu)
+        if (wk.step(rec_a + 48 * uu, sh_a + 4 * SHF * uu, row_a + 4 * ROWP * uu)) mask |= 1u << (j + uu);
+    }
+    const bool alive = __any_sync(FULL, wk.dead == 0.0f);
+    if (lane == 0) {
+      s_mask[s2 * NW + warp] = (unsigned char)mask;
+      s_alive[s2 * NW + warp] = alive ? 1 : 0;
+    }
+    __threadfence_block();  // this warp's accumulator rows / mask before its arrival
+    __syncwarp();
+    if (lane == 0) mbar_arrive(bar_done + 8 * s2);
+  }
+  if constexpr (STATS) {
+    const unsigned int wsum = __reduce_add_sync(FULL, wk.n_pairs);
+    if (p.stats && lane == 0 && wsum) atomicAdd(p.stats + 3, (unsigned long long)wsum);
+  }
 }
 
 
@@ -1120,84 +957,48 @@ static size_t fwd_smem() {
   return (size_t)2 * B * 3 * sizeof(float4) + (size_t)2 * B * 3 * C * C * sizeof(float) +
          (size_t)3 * B * sizeof(int);
 }
-template <int C, int B>
-static size_t bwd_smem() {
+template <int C>
+static size_t bwd3_smem() {
   constexpr int ROWP = (3 * C * C + 6 + 3) & ~3;
-  return (size_t)2 * B * 3 * sizeof(float4) + (size_t)2 * B * 3 * C * C * sizeof(float) +
-         (size_t)NWARPS * 9 * WROW * sizeof(float) + (size_t)2 * NWARPS * B * ROWP * sizeof(float) +
-         (size_t)4 * B * sizeof(int);
-}
-
-template <int C, int B, int NW, bool DIRECT>
-static size_t bwd2_smem() {
-  constexpr int ROWP = (3 * C * C + 6 + 3) & ~3;
-  return (size_t)2 * B * 3 * sizeof(float4) + (size_t)2 * B * 3 * C * C * sizeof(float) +
-         (size_t)NW * 9 * WROW * sizeof(float) +
-         (DIRECT ? (size_t)NW * ROWP : (size_t)2 * NW * B * ROWP) * sizeof(float) + (size_t)4 * B * sizeof(int);
+  return (size_t)RS * RG * 3 * sizeof(float4) + (size_t)RS * RG * 3 * C * C * sizeof(float) +
+         (size_t)NWARPS * 9 * WROW * sizeof(float) + (size_t)RS * NWARPS * RG * ROWP * sizeof(float) +
+         (size_t)2 * RS * RG * sizeof(int) + (size_t)RS * sizeof(int) + (size_t)2 * RS * NWARPS +
+         (size_t)2 * RS * sizeof(unsigned long long);
 }
 
 constexpr int FWD_B = 64;
 
-static int env_int(const char *name, int dflt) {
-  const char *v = getenv(name);
-  return v ? atoi(v) : dflt;
-}
-
-template <int C, int B, bool EXACT, bool RGB = false>
+template <int C, int B, bool EXACT, bool RGB, bool STATS>
 static int launch_fwd_t(const CompositeParams &p, uint32_t n_tiles, cudaStream_t st) {
   size_t sm = fwd_smem<C, B>();
-  GS3D_CUDA(cudaFuncSetAttribute(composite_fwd_kernel<C, B, EXACT, RGB>,
+  GS3D_CUDA(cudaFuncSetAttribute(composite_fwd_kernel<C, B, EXACT, RGB, STATS>,
                                  cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
-  composite_fwd_kernel<C, B, EXACT, RGB><<<n_tiles, NTHREADS, sm, st>>>(p);
+  composite_fwd_kernel<C, B, EXACT, RGB, STATS><<<n_tiles, NTHREADS, sm, st>>>(p);
   GS3D_LAUNCH_CHECK();
   return GS3D_OK;
 }
-template <int C>
+template <int C, bool RGB = false>
 static int launch_fwd(const CompositeParams &p, uint32_t n_tiles, cudaStream_t st) {
-  return p.exact ? launch_fwd_t<C, FWD_B, true>(p, n_tiles, st)
-                 : launch_fwd_t<C, FWD_B, false>(p, n_tiles, st);
+  if (p.stats)
+    return p.exact ? launch_fwd_t<C, FWD_B, true, RGB, true>(p, n_tiles, st)
+                   : launch_fwd_t<C, FWD_B, false, RGB, true>(p, n_tiles, st);
+  return p.exact ? launch_fwd_t<C, FWD_B, true, RGB, false>(p, n_tiles, st)
+                 : launch_fwd_t<C, FWD_B, false, RGB, false>(p, n_tiles, st);
 }
-template <int C, int B, bool EXACT, bool RGB = false>
+template <int C, bool EXACT, bool RGB, bool STATS>
 static int launch_bwd_t(const CompositeParams &p, uint32_t n_tiles, cudaStream_t st) {
-  size_t sm = bwd_smem<C, B>();
-  GS3D_CUDA(cudaFuncSetAttribute(composite_bwd_kernel<C, B, EXACT, RGB>,
+  size_t sm = bwd3_smem<C>();
+  GS3D_CUDA(cudaFuncSetAttribute(composite_bwd3_kernel<C, EXACT, RGB, STATS>,
                                  cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
-  composite_bwd_kernel<C, B, EXACT, RGB><<<n_tiles, NTHREADS, sm, st>>>(p);
+  composite_bwd3_kernel<C, EXACT, RGB, STATS><<<n_tiles, NTHREADS + 32, sm, st>>>(p);
   GS3D_LAUNCH_CHECK();
   return GS3D_OK;
 }
-template <int C, int B, bool EXACT, bool RGB, int NW, bool DIRECT>
-static int launch_bwd2_t(const CompositeParams &p, uint32_t n_tiles, cudaStream_t st) {
-  size_t sm = bwd2_smem<C, B, NW, DIRECT>();
-  GS3D_CUDA(cudaFuncSetAttribute(composite_bwd2_kernel<C, B, EXACT, RGB, NW, DIRECT>,
-                                 cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
-  composite_bwd2_kernel<C, B, EXACT, RGB, NW, DIRECT><<<n_tiles * (8 / NW), NW * 32, sm, st>>>(p);
-  GS3D_LAUNCH_CHECK();
-  return GS3D_OK;
-}
-
-template <int C>
+template <int C, bool RGB = false>
 static int launch_bwd(const CompositeParams &p, uint32_t n_tiles, cudaStream_t st) {
-#ifdef GS3D_BWD_EXPERIMENTS  // A/B builds (tools/ablate.sh): GS3D_BWD_VARIANT picks the kernel at run time
-  if constexpr (C == 4) {
-    static const int variant = env_int("GS3D_BWD_VARIANT", 0);
-    if (p.exact) switch (variant) {
-      case 1: return launch_bwd2_t<4, 16, true, false, 8, false>(p, n_tiles, st);  // uniform flow, accumulators
-      case 2: return launch_bwd2_t<4, 64, true, false, 8, true>(p, n_tiles, st);   // direct, barrier per 64
-      case 3: return launch_bwd2_t<4, 32, true, false, 8, true>(p, n_tiles, st);   // direct, barrier per 32
-      case 4: return launch_bwd2_t<4, 16, true, false, 4, false>(p, n_tiles, st);  // half tiles, accumulators
-      case 5: return launch_bwd2_t<4, 64, true, false, 4, true>(p, n_tiles, st);   // half tiles, direct
-      case 6: return launch_bwd2_t<4, 32, true, false, 4, false>(p, n_tiles, st);  // half tiles, accumulators, 32
-      default: break;
-    }
-  }
-#endif
-  // batch of 16 Gaussians -> 45 KB of shared memory and <= 85 registers: three CTAs per SM hide the
-  // barrier / warp-imbalance stalls better than two CTAs with 32 (measured: 1.45 vs 1.57 ms, cfg 2).
-  static const int bb = env_int("GS3D_BWD_B", 16);
-  if (bb == 16)
-    return p.exact ? launch_bwd_t<C, 16, true>(p, n_tiles, st) : launch_bwd_t<C, 16, false>(p, n_tiles, st);
-  return p.exact ? launch_bwd_t<C, 32, true>(p, n_tiles, st) : launch_bwd_t<C, 32, false>(p, n_tiles, st);
+  if (p.stats)  // measurement launches (gs3d_set_stage_counters): same kernel + pair counting
+    return p.exact ? launch_bwd_t<C, true, RGB, true>(p, n_tiles, st) : launch_bwd_t<C, false, RGB, true>(p, n_tiles, st);
+  return p.exact ? launch_bwd_t<C, true, RGB, false>(p, n_tiles, st) : launch_bwd_t<C, false, RGB, false>(p, n_tiles, st);
 }
 
 static bool aligned16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
@@ -1361,8 +1162,7 @@ int gs3d_composite_rgb_forward(uint32_t M, const float *records, const float *co
   if (rc) return rc;
   p.out = out;
   cudaStream_t st = as_stream(stream);
-  return exact_decisions ? launch_fwd_t<1, FWD_B, true, true>(p, n_tiles, st)
-                         : launch_fwd_t<1, FWD_B, false, true>(p, n_tiles, st);
+  return launch_fwd<1, true>(p, n_tiles, st);
 }
 
 int gs3d_composite_rgb_backward(uint32_t M, const float *records, const float *color, const int32_t *start,
@@ -1384,8 +1184,7 @@ int gs3d_composite_rgb_backward(uint32_t M, const float *records, const float *c
   p.g_mean = grad_mean2d; p.g_cov = grad_cov2d; p.g_sh = grad_color; p.g_alpha = grad_alpha;
   p.gsh_sg = 3; p.gsh_sc = 1; p.gsh_vec = 0;
   cudaStream_t st = as_stream(stream);
-  return exact_decisions ? launch_bwd_t<1, 16, true, true>(p, n_tiles, st)
-                         : launch_bwd_t<1, 16, false, true>(p, n_tiles, st);
+  return launch_bwd<1, true>(p, n_tiles, st);
 }
 
 }  // extern "C"

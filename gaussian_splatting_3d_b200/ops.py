@@ -464,11 +464,11 @@ def image_loss(out, gt, base="l2", ssim_mult=0.0, window_size=11, want_grad=True
 
 # ---------------------------------------------------------------- measurement aid
 def set_stage_counters(counters):
-    """counters: int64 [2] CUDA tensor (zeroed) or None; see gs3d_set_stage_counters."""
+    """counters: int64 [4] CUDA tensor (zeroed) or None; see gs3d_set_stage_counters."""
     if counters is not None:
         _chk(counters, "counters", _I64)
-        if counters.numel() < 2:
-            raise RuntimeError("counters must hold two int64 values")
+        if counters.numel() < 4:
+            raise RuntimeError("counters must hold four int64 values")
     check(capi.lib.gs3d_set_stage_counters(ptr(counters)), "set_stage_counters")
 
 

@@ -283,10 +283,13 @@ int gs3d_clip_rects_to_rows(uint32_t N, const int32_t *aabb_topleft, const int32
                             int32_t *br_out, float *depth_out, int32_t *index_out, int64_t *counts_host,
                             void *scratch, size_t scratch_bytes, void *stream);
 
-/* ---- measurement aid: when set (device pointer to two zero-initialised uint64 counters, NULL to
+/* ---- measurement aid: when set (device pointer to FOUR zero-initialised uint64 counters, NULL to
  * disable), every compositing launch adds the number of duplicates it actually STAGED into shared
- * memory to counters[0] (forward) / counters[1] (backward) -- one atomic per tile.  Tiles stop staging
- * once all their pixels are saturated, so this is the unit count behind bench.py's roofline. */
+ * memory to counters[0] (forward) / counters[1] (backward) -- one atomic per tile -- and the number of
+ * CONTRIBUTING (pixel, Gaussian) pairs (alpha*G >= 1/255, pixel not yet saturated) to counters[2] (forward) /
+ * counters[3] (backward).  Tiles stop staging once all their pixels are saturated, so these are the unit
+ * counts behind bench.py's rooflines (bytes per staged duplicate, FLOP per pair).  Launches made while the
+ * counters are set run an instrumented instantiation of the same kernels. */
 int gs3d_set_stage_counters(uint64_t *counters);
 
 /* ======== the steps either side of the rasteriser in the training loop ======== */

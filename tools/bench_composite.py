@@ -62,6 +62,23 @@ def timeit(fn):
     return ts[len(ts) // 2]
 
 
-res = {"lib": os.environ.get("GS3D_LIB", "default"), "cfg": name, "fwd_ms": round(timeit(fwd), 4),
-       "bwd_ms": round(timeit(bwd), 4), "img_sum": float(out.sum())}
+res = {"lib": os.environ.get("GS3D_LIB", "default"), "variant": os.environ.get("GS3D_BWD_VARIANT", ""), "cfg": name,
+       "fwd_ms": round(timeit(fwd), 4)}
+gout = (2.0 * (out - torch.rand(H * W * 3, device=dev, generator=torch.Generator(dev).manual_seed(1))) / out.numel())
+res["bwd_ms"] = round(timeit(bwd), 4)
+# gradient fingerprint of ONE backward from zeroed buffers (A/B builds must agree to float-atomics noise)
+for t in (gm, gc, gsh, ga):
+    t.zero_()
+bwd()
+torch.cuda.synchronize()
+res["img_sum"] = float(out.sum())
+res["grad_norms"] = [float(t.double().norm()) for t in (gm, gc, gsh, ga)]
+ref_path = os.environ.get("GS3D_GRAD_REF")
+if ref_path:
+    if os.path.exists(ref_path):
+        ref = torch.load(ref_path, map_location=dev)
+        res["grad_rel_vs_ref"] = [float((a.double() - b.double()).norm() / b.double().norm().clamp_min(1e-30))
+                                  for a, b in zip((gm, gc, gsh, ga), ref)]
+    else:
+        torch.save([gm, gc, gsh, ga], ref_path)
 print(json.dumps(res))
