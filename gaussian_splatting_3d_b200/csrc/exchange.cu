@@ -193,56 +193,130 @@ struct PullArgs {
   float *dst_peer[8];
 };
 
+// One warp per 512-row chunk of the union marks.  The marked rows of the chunk are first compacted into a
+// list in shared memory; the warp then walks the (row, 16-byte unit) pairs with FOUR independent
+// multimem.ld_reduce in flight per lane before the matching stores, so the NVSwitch round trip (~3 us) is
+// overlapped ~128-fold per warp instead of being paid once per row (the first version did one row at a time:
+// 125-150 GB/s per GPU; profiles/r2_exchange_pull.txt).
+__device__ __forceinline__ float4 pull_load_v4(const PullArgs &a, size_t e) {
+  float4 v;
+  if (a.src_mc) {
+    asm volatile("multimem.ld_reduce.relaxed.sys.global.add.v4.f32 {%0, %1, %2, %3}, [%4];"
+                 : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(a.src_mc + e));
+  } else {
+    v = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int r = 0; r < a.n_peers; ++r) {
+      float4 t;
+      asm volatile("ld.relaxed.sys.global.v4.f32 {%0, %1, %2, %3}, [%4];"
+                   : "=f"(t.x), "=f"(t.y), "=f"(t.z), "=f"(t.w) : "l"(a.src_peer[r] + e));
+      v.x += t.x; v.y += t.y; v.z += t.z; v.w += t.w;
+    }
+  }
+  return v;
+}
+__device__ __forceinline__ void pull_store_v4(const PullArgs &a, size_t e, float4 v) {
+  if (a.dst_mc) {
+    asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(a.dst_mc + e), "f"(v.x),
+                 "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+  } else {
+    for (int r = 0; r < a.n_peers; ++r) *reinterpret_cast<float4 *>(a.dst_peer[r] + e) = v;
+  }
+}
+__device__ __forceinline__ float pull_load_f32(const PullArgs &a, size_t e) {
+  float v;
+  if (a.src_mc) {
+    asm volatile("multimem.ld_reduce.relaxed.sys.global.add.f32 %0, [%1];" : "=f"(v) : "l"(a.src_mc + e));
+  } else {
+    v = 0.f;
+    for (int r = 0; r < a.n_peers; ++r) {
+      float t;
+      asm volatile("ld.relaxed.sys.global.f32 %0, [%1];" : "=f"(t) : "l"(a.src_peer[r] + e));
+      v += t;
+    }
+  }
+  return v;
+}
+__device__ __forceinline__ void pull_store_f32(const PullArgs &a, size_t e, float v) {
+  if (a.dst_mc) {
+    asm volatile("multimem.st.relaxed.sys.global.f32 [%0], %1;" ::"l"(a.dst_mc + e), "f"(v) : "memory");
+  } else {
+    for (int r = 0; r < a.n_peers; ++r) a.dst_peer[r][e] = v;
+  }
+}
+
+constexpr int PULL_MLP = 4;   // independent loads per lane
+constexpr int PULL_MAX_UNITS = 64;
+
 __global__ void __launch_bounds__(256)
 rows_pull_kernel(const PullArgs a) {
-  const int lane = threadIdx.x & 31;
-  for_each_marked(a.union_marks, a.N, 0, [&](size_t g) {
-    for (int u = lane; u < a.n_units; u += 32) {
-      int s = 0;
-      while (s + 1 < a.n_seg && (uint32_t)u >= a.unit0[s + 1]) ++s;
-      const uint32_t k = u - a.unit0[s];
-      if (a.vec[s]) {
-        const size_t e = a.off[s] + g * a.width[s] + 4 * k;
-        float4 v;
-        if (a.src_mc) {
-          asm volatile("multimem.ld_reduce.relaxed.sys.global.add.v4.f32 {%0, %1, %2, %3}, [%4];"
-                       : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(a.src_mc + e) : "memory");
-        } else {
-          v = make_float4(0.f, 0.f, 0.f, 0.f);
-          for (int r = 0; r < a.n_peers; ++r) {
-            float4 t;
-            asm volatile("ld.relaxed.sys.global.v4.f32 {%0, %1, %2, %3}, [%4];"
-                         : "=f"(t.x), "=f"(t.y), "=f"(t.z), "=f"(t.w) : "l"(a.src_peer[r] + e) : "memory");
-            v.x += t.x; v.y += t.y; v.z += t.z; v.w += t.w;
-          }
-        }
-        if (a.dst_mc) {
-          asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(a.dst_mc + e), "f"(v.x),
-                       "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
-        } else {
-          for (int r = 0; r < a.n_peers; ++r) *reinterpret_cast<float4 *>(a.dst_peer[r] + e) = v;
-        }
-      } else {
-        const size_t e = a.off[s] + g * a.width[s] + k;
-        float v;
-        if (a.src_mc) {
-          asm volatile("multimem.ld_reduce.relaxed.sys.global.add.f32 %0, [%1];" : "=f"(v) : "l"(a.src_mc + e) : "memory");
-        } else {
-          v = 0.f;
-          for (int r = 0; r < a.n_peers; ++r) {
-            float t;
-            asm volatile("ld.relaxed.sys.global.f32 %0, [%1];" : "=f"(t) : "l"(a.src_peer[r] + e) : "memory");
-            v += t;
-          }
-        }
-        if (a.dst_mc) {
-          asm volatile("multimem.st.relaxed.sys.global.f32 [%0], %1;" ::"l"(a.dst_mc + e), "f"(v) : "memory");
-        } else {
-          for (int r = 0; r < a.n_peers; ++r) a.dst_peer[r][e] = v;
-        }
+  __shared__ uint16_t s_rows[8][512];
+  __shared__ uint32_t s_unit[PULL_MAX_UNITS];  // per unit: segment | offset-in-row << 8 | vec << 31
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  for (int u = threadIdx.x; u < a.n_units; u += blockDim.x) {
+    int sg = 0;
+    while (sg + 1 < a.n_seg && (uint32_t)u >= a.unit0[sg + 1]) ++sg;
+    const uint32_t k = u - a.unit0[sg];
+    s_unit[u] = (uint32_t)sg | ((a.vec[sg] ? 4 * k : k) << 8) | (a.vec[sg] ? 0x80000000u : 0u);
+  }
+  __syncthreads();
+  const uint32_t chunk = (blockIdx.x * 8 + wib) * (uint32_t)a.n_peers + (uint32_t)a.rank;
+  if ((size_t)chunk * 512 >= a.N) return;
+  // ---- compact the marked rows of this chunk (lane owns 16 consecutive marks)
+  const size_t c0 = (size_t)chunk * 512 + (size_t)lane * 16;
+  uint32_t bits = 0;  // bit b: mark c0 + b is set
+  if (c0 + 16 <= a.N && ((reinterpret_cast<uintptr_t>(a.union_marks) & 15) == 0)) {
+    const uint4 v = *reinterpret_cast<const uint4 *>(a.union_marks + c0);
+    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+    for (int q = 0; q < 4; ++q)
+#pragma unroll
+      for (int b = 0; b < 4; ++b)
+        if ((w[q] >> (8 * b)) & 0xffu) bits |= 1u << (4 * q + b);
+  } else {
+    for (int b = 0; b < 16; ++b)
+      if (c0 + b < a.N && a.union_marks[c0 + b]) bits |= 1u << b;
+  }
+  uint32_t cnt = __popc(bits), incl = cnt;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const uint32_t y = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl += y;
+  }
+  const uint32_t n_rows = __shfl_sync(0xffffffffu, incl, 31);
+  uint32_t pos = incl - cnt;
+  while (bits) {
+    const int b = __ffs(bits) - 1;
+    bits &= bits - 1;
+    s_rows[wib][pos++] = (uint16_t)(lane * 16 + b);
+  }
+  __syncwarp();
+  if (n_rows == 0) return;
+  const size_t row0 = (size_t)chunk * 512;
+  const uint32_t total = n_rows * (uint32_t)a.n_units;
+  for (uint32_t i0 = 0; i0 < total; i0 += 32 * PULL_MLP) {
+    float4 v[PULL_MLP];
+    size_t e[PULL_MLP];
+    uint32_t kind[PULL_MLP];  // 0 = none, 1 = scalar, 2 = vector
+#pragma unroll
+    for (int m = 0; m < PULL_MLP; ++m) {
+      const uint32_t i = i0 + 32 * m + lane;
+      kind[m] = 0;
+      if (i < total) {
+        const uint32_t r = i / (uint32_t)a.n_units, u = i - r * (uint32_t)a.n_units;
+        const uint32_t info = s_unit[u];
+        const uint32_t sg = info & 0xffu, k = (info >> 8) & 0x7fffffu;
+        const size_t g = row0 + s_rows[wib][r];
+        e[m] = a.off[sg] + g * a.width[sg] + k;
+        if (info >> 31) { kind[m] = 2; v[m] = pull_load_v4(a, e[m]); }
+        else { kind[m] = 1; v[m].x = pull_load_f32(a, e[m]); }
       }
     }
-  }, (uint32_t)a.n_peers, (uint32_t)a.rank);
+#pragma unroll
+    for (int m = 0; m < PULL_MLP; ++m) {
+      if (kind[m] == 2) pull_store_v4(a, e[m], v[m]);
+      else if (kind[m] == 1) pull_store_f32(a, e[m], v[m].x);
+    }
+  }
 }
 
 struct MarkArgs {
@@ -394,6 +468,8 @@ int gs3d_rows_pull_marked(uint8_t *union_marks, uint32_t N, int n_blocks, const 
     units += a.vec[s] ? a.width[s] / 4 : a.width[s];
   }
   a.n_units = (int)units;
+  GS3D_REQUIRE(units <= (uint32_t)PULL_MAX_UNITS, GS3D_EUNSUPPORTED, "rows_pull: %u units per row (max %d)", units,
+               PULL_MAX_UNITS);
   const uint32_t chunks = div_up(N, 512u);
   rows_pull_kernel<<<div_up(div_up(chunks, (uint32_t)n_peers), 8u), 256, 0, as_stream(stream)>>>(a);
   GS3D_LAUNCH_CHECK();

@@ -58,7 +58,9 @@ class FlatGradients:
                  sparse_reset=False):
         self.names = list(self.ORDER)
         self.params = [getattr(module, n) for n in self.names]
-        total = sum(p.numel() for p in self.params)
+        # every block starts on a 16-byte boundary (the kernels use float4 accesses on qvec gradients and
+        # vector reductions on SH rows; an unpadded layout is only aligned when N is a multiple of 4)
+        total = sum((p.numel() + 3) // 4 * 4 for p in self.params)
         dev = self.params[0].device
         N = self.params[0].size(0)
         self.group = group
@@ -81,7 +83,7 @@ class FlatGradients:
             for p in self.params:
                 views.append(buf[off:off + p.numel()].view_as(p))
                 offsets.append(off)
-                off += p.numel()
+                off += (p.numel() + 3) // 4 * 4
             return views, offsets
 
         self.peer_ptrs = None

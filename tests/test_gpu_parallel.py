@@ -231,6 +231,83 @@ def test_two_gpu_sparse_gradient_exchange(mode):
         assert nz_rows <= union_rows < N
 
 
+def _worker_adc(rank, world, port, q):
+    """view_sharded_step -> adaptive_control(force=True) (split + prune + alpha reset: N changes, the ADC
+    buffers are replaced) -> view_sharded_step again, on both ranks."""
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dev = f"cuda:{rank}"
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device(dev))
+    import math
+
+    from gaussian_splatting_3d_b200 import parallel as P
+
+    sc = S.make_scene("cfg3", seed=0, N=40_000, C=2)
+    cam = S.make_camera("cfg3")
+    r = S.renderer_from_scene(sc, S.make_cfg(device=dev, sh_order=2, warm_up=0, pos_grad_thresh=1e-7))
+    r.train()
+    r.fuse_adc = True
+    c2ws = []
+    for i in range(4):
+        a = math.radians(3.0 * (i - 1.5))
+        c2ws.append(torch.tensor([[math.cos(a), 0, math.sin(a), 0], [0, 1, 0, 0], [-math.sin(a), 0, math.cos(a), 0]],
+                                 dtype=torch.float32, device=dev))
+    targets = [S.make_target(cam, i).to(dev) for i in range(4)]
+    flat = P.FlatGradients(r, pull=True).attach(r)
+    P.view_sharded_step(r, flat, c2ws, cam, targets)
+    cnt1, gm1 = r.cnt.clone(), r.grad_mean.clone()
+    n0 = r.N
+    torch.manual_seed(123)  # the split draws torch.randn: same stream on both ranks
+    r.adaptive_control(0, force=True)
+    n1 = r.N
+    stale = None
+    try:
+        flat.zero()
+    except RuntimeError as e:
+        stale = str(e)
+    flat = P.FlatGradients(r, pull=True).attach(r)  # the owner rebuilds the buffers for the new parameters
+    P.view_sharded_step(r, flat, c2ws, cam, targets)
+    # serial reference of the second step's statistics on this rank
+    r2 = S.renderer_from_scene({k: (getattr(r, k).data.cpu() if k in ("mean", "qvec", "svec_before_activation", "sh_coeffs",
+                                                                    "alpha_before_activation") else v)
+                                for k, v in sc.items()},
+                               S.make_cfg(device=dev, sh_order=2, warm_up=0))
+    r2.now_C = r.now_C
+    r2.train()
+    r2.fuse_adc = True
+    for i in range(4):
+        ((r2(c2ws[i], cam) - targets[i]) ** 2).mean().backward()
+    gm_rel = float((r.grad_mean.double() - r2.grad_mean.double()).norm() / r2.grad_mean.double().norm().clamp_min(1e-30))
+    q.put((rank, n0, n1, stale is not None, bool(torch.equal(r.cnt, r2.cnt)), gm_rel, int(cnt1.max()), float(gm1.sum()),
+           int(r.mean.data.sum().item() * 1000)))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
+def test_two_gpu_view_sharded_training_across_adaptive_control():
+    """sync_adc's per-renderer baseline and the attached gradient views must not survive a change
+    of N -- statistics after the density-control step equal the serial ones, stale buffers raise."""
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 30100 + (os.getpid() % 2000)
+    procs = [ctx.Process(target=_worker_adc, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted([q.get(timeout=300) for _ in range(2)])
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for rank, n0, n1, stale_raised, cnt_ok, gm_rel, cnt_max, gm_sum, chk in res:
+        print(f"[adc dp rank {rank}] N {n0} -> {n1}, stale buffers rejected: {stale_raised}, cnt ok {cnt_ok}, "
+              f"grad_mean rel {gm_rel:.2e}")
+        assert n1 != n0 and stale_raised
+        assert cnt_max == 4 and gm_sum > 0      # first step: four views counted on every rank
+        assert cnt_ok and gm_rel < 1e-3
+    assert res[0][1:3] == res[1][1:3] and res[0][-1] == res[1][-1]  # both ranks hold the same model
+
+
 @pytest.mark.gpu
 def test_rows_gather_scatter_roundtrip():
     from gaussian_splatting_3d_b200 import ops

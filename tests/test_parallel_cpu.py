@@ -106,3 +106,93 @@ def test_view_sharded_gradient_allreduce_gloo_world2():
     assert torch.allclose(f0, want, rtol=1e-5, atol=1e-5)
     assert torch.equal(gm0, gm1) and float(gm0[0]) == float(sum(range(1, 9)))
     assert torch.equal(c0, c1) and int(c0[0]) == 8
+
+
+def _worker_adc_baseline(rank, world, port, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+
+    class M:
+        pass
+
+    m = M()
+    m.split_reduction, m.split_type = "mean", "2d_mean_grad"
+    m.grad_mean, m.cnt, m._adc_epoch = torch.zeros(6), torch.zeros(6, dtype=torch.int32), 1
+    out = []
+    # step 1: rank-distinct contributions
+    m.grad_mean += float(rank + 1)
+    m.cnt += 1
+    P.sync_adc(m)
+    out.append((m.grad_mean.clone(), m.cnt.clone()))
+    # step 2 accumulates on top of the synchronised state
+    m.grad_mean += float(rank + 1)
+    m.cnt += 1
+    P.sync_adc(m)
+    out.append((m.grad_mean.clone(), m.cnt.clone()))
+    # density control: N changes and the buffers are replaced (SHRenderer._reset_adc_buffers bumps the epoch)
+    m.grad_mean, m.cnt, m._adc_epoch = torch.zeros(9), torch.zeros(9, dtype=torch.int32), 2
+    m.grad_mean += float(rank + 1)
+    m.cnt += 1
+    P.sync_adc(m)
+    out.append((m.grad_mean.clone(), m.cnt.clone()))
+    # an alpha reset keeps N but re-zeroes the buffers: the stale baseline must not be subtracted
+    m.grad_mean, m.cnt, m._adc_epoch = torch.zeros(9), torch.zeros(9, dtype=torch.int32), 3
+    m.grad_mean += float(rank + 1)
+    m.cnt += 1
+    P.sync_adc(m)
+    out.append((m.grad_mean.clone(), m.cnt.clone()))
+    # split_type mean_grad: the statistic comes from the already exchanged gradient -> identical on all ranks, not summed
+    m.split_type = "mean_grad"
+    m.grad_mean += 5.0
+    m.cnt += 1
+    P.sync_adc(m)
+    out.append((m.grad_mean.clone(), m.cnt.clone()))
+    q.put((rank, out))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_sync_adc_baseline_follows_buffer_resets_gloo_world2():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 31500 + (os.getpid() % 2000)
+    procs = [ctx.Process(target=_worker_adc_baseline, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted([q.get(timeout=120) for _ in range(2)], key=lambda t: t[0])
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for (gm0, c0), (gm1, c1) in zip(res[0][1], res[1][1]):
+        assert torch.equal(gm0, gm1) and torch.equal(c0, c1)
+    o = res[0][1]
+    assert float(o[0][0][0]) == 3.0 and int(o[0][1][0]) == 2      # 1 + 2, two views
+    assert float(o[1][0][0]) == 6.0 and int(o[1][1][0]) == 4
+    assert o[2][0].numel() == 9 and float(o[2][0][0]) == 3.0 and int(o[2][1][0]) == 2   # fresh after the split
+    assert float(o[3][0][0]) == 3.0 and int(o[3][1][0]) == 2                          # fresh after the alpha reset
+    assert float(o[4][0][0]) == 8.0 and int(o[4][1][0]) == 4                          # +5 once, cnt +1 per rank
+
+
+def test_stale_gradient_views_are_rejected():
+    """a renderer that replaced its parameters drops the attached gradient views, and the
+    FlatGradients that owned them refuses to be used again."""
+
+    class M(torch.nn.Module):
+        pass
+
+    m = M()
+    for n, shape in (("mean", (5, 3)), ("qvec", (5, 4)), ("svec_before_activation", (5, 3)), ("sh_coeffs", (5, 3, 4)),
+                     ("alpha_before_activation", (5,))):
+        setattr(m, n, torch.nn.Parameter(torch.zeros(shape)))
+    m.grad_buffers = None
+    flat = P.FlatGradients(m).attach(m)
+    flat.zero()
+    m.mean = torch.nn.Parameter(torch.zeros(7, 3))  # what _set_params does ...
+    m.grad_buffers = None                           # ... including dropping the views
+    try:
+        flat.zero()
+        raised = False
+    except RuntimeError:
+        raised = True
+    assert raised
