@@ -37,6 +37,9 @@ def parse():
                     help="cfg2 (default): one view per rank per step, weak scaling.  cfg4 (SURVEY 8d): the cfg-2 scene, "
                          "8 ring cameras per step, 8/G cameras per rank, gradients exchanged -- strong scaling.  cfg5: "
                          "6 M Gaussians at 3840x2160, forward only, tile rows sharded over the ranks -- strong scaling")
+    ap.add_argument("--no-graph", action="store_true",
+                    help="time the eager step (one 8-byte read-back of the duplicate count per forward, ~40 launches) "
+                         "instead of the CUDA-graph step (graph.GraphedStep; single-GPU single-view workloads)")
     ap.add_argument("--check", action="store_true",
                     help="after timing: whole-path parity of this workload against the reference GPU flow "
                          "(oracle/fullsize_check.py; needs oracle/_ref) added to the line as `parity`")
@@ -352,13 +355,35 @@ def run_ours(args, rank, local_rank, world):
         fwd_only()
     torch.cuda.synchronize()
 
+    # single-GPU, one view per step: the product's fast path is the CUDA-graph step (static duplicate capacity, no
+    # host round trip, two graph launches per step); `--no-graph` times the eager step instead
+    ms_fwd = timed(fwd_only, args.steps)  # forward-only FPS: the eager render call (viewer / evaluation loop)
+    gstep = None
+    if world == 1 and not cfg4 and not args.no_graph:
+        from gaussian_splatting_3d_b200.graph import GraphedStep
+
+        gstep = GraphedStep(r, flat, cam)
+        gstep(c2w_devs[0], tgt_devs[0])  # capture
+        gstep.target.copy_(tgt_devs[0])
+        gstep.check()
+        torch.cuda.synchronize()
+    l0 = capi.lib.gs3d_launch_count()
+    step(False)
+    launches_per_step = capi.lib.gs3d_launch_count() - l0
     with ClockSampler(phys_gpu_index(local_rank)) as clk:
-        l0 = capi.lib.gs3d_launch_count()
-        ms_total = timed(lambda: step(False), args.steps)
-        launches = capi.lib.gs3d_launch_count() - l0
-        ms_e2e = timed(lambda: step(True), args.steps)
-        ms_fwd = timed(fwd_only, args.steps)
+        if gstep is not None:
+            r.static_capacity = gstep.capacity
+            ms_total = timed(lambda: gstep(c2w_devs[0], gstep.target), args.steps)
+            ms_e2e = timed(lambda: gstep(c2w_hosts[0], tgt_hosts[0], read_loss=True), args.steps)
+            gstep.check()
+            r.static_capacity = None
+        else:
+            ms_total = timed(lambda: step(False), args.steps)
+            ms_e2e = timed(lambda: step(True), args.steps)
+        launches = launches_per_step * args.steps  # kernels executed in the timed region (graph nodes included)
     clocks = clk.summary()
+    for _ in range(2):  # (graph capture emptied the allocator cache: refill it before the per-stage event timing)
+        step(False)
 
     # ---- per-stage CUDA-event times (same stream the kernels are launched on)
     stage_ms = {}
@@ -444,7 +469,11 @@ def run_ours(args, rank, local_rank, world):
                          "gradient_buffers": "one persistent flat buffer aliased by .grad; per-step reset clears "
                                              "only the rows the previous backward marked",
                          "l2_policy": "inputs larger than L2 (parameters 708 MB, duplicates 132 MB vs 126 MB L2)",
-                         "exact_decisions": not args.no_exact},
+                         "exact_decisions": not args.no_exact,
+                         "step_launch": ("2 CUDA-graph launches per step (graph.GraphedStep: static capacity "
+                                         f"{gstep.capacity} duplicates, no host round trip)" if gstep is not None
+                                         else "eager: one 8-byte read-back of the duplicate count per forward"),
+                         "kernels_per_step": int(launches_per_step)},
         "fwd_fps": world * 1000.0 * args.steps / ms_fwd,
         "kernels_ms": kernels_ms,
         "rank_kernel_ms": rank_kernel_ms,

@@ -55,10 +55,12 @@ SIGNATURES = {
     "gs3d_count_scratch_bytes": (_sz, [_u32]),
     "gs3d_tile_culling_aabb_count": (_i, [_u32, _P, _P, _u32, _CAM, _f, _P, _P, _I64P, _P, _sz, _P]),
     "gs3d_project_cull_fused": (_i, [_u32, _P, _P, _P, _P, _i, _i, _P, _CAM, _f, _i, _f, _u32,
-                                     _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I64P, _P, _sz, _P]),
+                                     _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _sz, _P]),
     "gs3d_binning_scratch_bytes": (_sz, [_u32, _u32]),
     "gs3d_tile_culling_aabb_start_end": (_i, [_u32, _u32, _u32, _u32, _P, _P, _P, _P, _P, _P, _P,
                                               _i, _P, _sz, _P]),
+    "gs3d_tile_culling_aabb_start_end_capacity": (_i, [_u32, _u32, _u32, _u32, _P, _P, _P, _P, _P, _P, _P, _P,
+                                                       _P, _sz, _P]),
     "gs3d_pack_records": (_i, [_u32, _P, _P, _P, _P, _P, _P]),
     "gs3d_composite_sh_forward": (_i, [_u32, _P, _P, _u32, _u32, _P, _P, _P, _P, _P, _P, _u32, _u32,
                                        _u32, _f, _f, _u32, _u32, _u32, _f, _P, _P, _P, _i, _P]),

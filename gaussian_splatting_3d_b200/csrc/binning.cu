@@ -29,8 +29,9 @@ constexpr int SORT_WARPS = SORT_THREADS / 32;
 __global__ void __launch_bounds__(SORT_THREADS)
 radix_hist_kernel(const uint32_t *__restrict__ keys, uint32_t n, int shift, uint32_t mask,
                   uint32_t nblocks, uint32_t *__restrict__ table /*[RADIX][nblocks]*/,
-                  uint32_t *__restrict__ totals /*[RADIX]*/) {
+                  uint32_t *__restrict__ totals /*[RADIX]*/, const uint32_t *__restrict__ n_dev) {
   __shared__ uint32_t h[RADIX];
+  if (n_dev) n = min(n, *n_dev);  // capacity-sized launch: the real item count lives on the device
   h[threadIdx.x] = 0;
   __syncthreads();
   size_t base = (size_t)blockIdx.x * SORT_TILE;
@@ -104,8 +105,10 @@ __global__ void __launch_bounds__(SORT_THREADS, 3)
 radix_scatter_kernel(const uint32_t *__restrict__ keys_in, const uint32_t *__restrict__ vals_in,
                      uint32_t *__restrict__ keys_out, uint32_t *__restrict__ vals_out, uint32_t n,
                      int shift, uint32_t mask, uint32_t nblocks,
-                     const uint32_t *__restrict__ table) {
+                     const uint32_t *__restrict__ table, const uint32_t *__restrict__ n_dev) {
   __shared__ uint32_t s_keys[SORT_TILE];
+  if (n_dev) n = min(n, *n_dev);
+  if ((size_t)blockIdx.x * SORT_TILE >= n) return;  // (whole block: uniform)
   __shared__ uint32_t s_vals[SORT_TILE];
   __shared__ uint32_t warp_hist[SORT_WARPS][RADIX];  // per-warp running digit counts
   __shared__ uint32_t digit_base[RADIX];             // exclusive scan of block digit totals
@@ -414,21 +417,22 @@ static int onesweep_pass(const uint32_t *kin, const uint32_t *vin, uint32_t *kou
 }
 
 static int radix_pass(const uint32_t *kin, const uint32_t *vin, uint32_t *kout, uint32_t *vout,
-                      uint32_t n, int shift, int bits, const RadixBuffers &rb, cudaStream_t st) {
+                      uint32_t n, int shift, int bits, const RadixBuffers &rb, cudaStream_t st,
+                      const uint32_t *n_dev = nullptr) {
   uint32_t nblocks = div_up(n, (uint32_t)SORT_TILE);
   uint32_t mask = (1u << bits) - 1u;
   GS3D_CUDA(cudaMemsetAsync(rb.totals, 0, RADIX * sizeof(uint32_t), st));
-  radix_hist_kernel<<<nblocks, SORT_THREADS, 0, st>>>(kin, n, shift, mask, nblocks, rb.table, rb.totals);
+  radix_hist_kernel<<<nblocks, SORT_THREADS, 0, st>>>(kin, n, shift, mask, nblocks, rb.table, rb.totals, n_dev);
   GS3D_LAUNCH_CHECK();
   radix_scan_kernel<<<RADIX, 256, 0, st>>>(nblocks, rb.table, rb.totals);
   GS3D_LAUNCH_CHECK();
   static const bool ballot = [] { const char *e = getenv("GS3D_RANK"); return !(e && e[0] == 'm'); }();
   if (ballot)
     radix_scatter_kernel<true><<<nblocks, SORT_THREADS, 0, st>>>(kin, vin, kout, vout, n, shift, mask,
-                                                                 nblocks, rb.table);
+                                                                 nblocks, rb.table, n_dev);
   else
     radix_scatter_kernel<false><<<nblocks, SORT_THREADS, 0, st>>>(kin, vin, kout, vout, n, shift, mask,
-                                                                  nblocks, rb.table);
+                                                                  nblocks, rb.table, n_dev);
   GS3D_LAUNCH_CHECK();
   return GS3D_OK;
 }
@@ -495,7 +499,9 @@ count_sorted_kernel(uint32_t N, const uint32_t *__restrict__ sorted_ids,
 
 // single block: exclusive scan of block_sums in place, grand total to *total
 __global__ void __launch_bounds__(1024)
-scan_block_sums_kernel(uint32_t nb, uint32_t *__restrict__ block_sums, uint32_t *__restrict__ total) {
+scan_block_sums_kernel(uint32_t nb, uint32_t *__restrict__ block_sums, uint32_t *__restrict__ total,
+                       uint32_t capacity, uint32_t *__restrict__ n_eff, int64_t *__restrict__ n_dub_out,
+                       int32_t *__restrict__ overflow) {
   __shared__ uint32_t wsum[32];
   __shared__ uint32_t carry_s;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -520,7 +526,13 @@ scan_block_sums_kernel(uint32_t nb, uint32_t *__restrict__ block_sums, uint32_t 
     if (threadIdx.x == 1023) carry_s = carry + wb + incl;
     __syncthreads();
   }
-  if (threadIdx.x == 0) *total = carry_s;
+  if (threadIdx.x == 0) {
+    const uint32_t t = carry_s;
+    *total = t;
+    if (n_eff) *n_eff = min(t, capacity);           // what the duplicate-level kernels process
+    if (n_dub_out) *n_dub_out = (int64_t)t;         // the true count (the reference's N_with_dub)
+    if (overflow) *overflow = t > capacity ? 1 : 0; // the caller's id buffer was too small: result truncated
+  }
 }
 
 // Emit (tile, id) pairs in depth order; x outer, y inner like aabb_culling.h:29-38.  Offsets come
@@ -530,9 +542,10 @@ __global__ void __launch_bounds__(256)
 emit_kernel(uint32_t N, uint32_t n_dub, uint32_t n_tiles_w, const uint32_t *__restrict__ sorted_ids,
             const int32_t *__restrict__ tl, const int32_t *__restrict__ br,
             const uint32_t *__restrict__ block_offsets, uint32_t *__restrict__ keys,
-            uint32_t *__restrict__ vals) {
+            uint32_t *__restrict__ vals, const uint32_t *__restrict__ n_dev) {
   __shared__ uint32_t sm[8];
   constexpr uint32_t SMALL = 8;
+  if (n_dev) n_dub = min(n_dub, *n_dev);
   uint32_t j = blockIdx.x * 256 + threadIdx.x;
   uint32_t c = 0, g = 0;
   int tlx = 0, tly = 0, h = 1;
@@ -574,7 +587,8 @@ emit_kernel(uint32_t N, uint32_t n_dub, uint32_t n_tiles_w, const uint32_t *__re
 
 __global__ void __launch_bounds__(256)
 ranges_kernel(uint32_t n_dub, const uint32_t *__restrict__ tile_keys, int32_t *__restrict__ start,
-              int32_t *__restrict__ end, uint32_t n_tiles) {
+              int32_t *__restrict__ end, uint32_t n_tiles, const uint32_t *__restrict__ n_dev) {
+  if (n_dev) n_dub = min(n_dub, *n_dev);
   // four consecutive keys per thread (one 16-byte load) plus the two neighbours
   const size_t g0 = 4 * ((size_t)blockIdx.x * 256 + threadIdx.x);
   if (g0 >= n_dub) return;
@@ -603,7 +617,8 @@ ranges_kernel(uint32_t n_dub, const uint32_t *__restrict__ tile_keys, int32_t *_
 __global__ void __launch_bounds__(256)
 keys64_kernel(uint32_t n_dub, const uint32_t *__restrict__ tile_keys,
               const int32_t *__restrict__ ids, const float *__restrict__ depth,
-              int64_t *__restrict__ keys64) {
+              int64_t *__restrict__ keys64, const uint32_t *__restrict__ n_dev) {
+  if (n_dev) n_dub = min(n_dub, *n_dev);
   uint32_t g = blockIdx.x * 256 + threadIdx.x;
   if (g >= n_dub) return;
   uint64_t k = ((uint64_t)tile_keys[g] << 32) | (uint64_t)__float_as_uint(depth[ids[g]]);
@@ -633,13 +648,14 @@ size_t gs3d_binning_scratch_bytes(uint32_t N, uint32_t n_dub) {
   return b + 1024;
 }
 
-int gs3d_tile_culling_aabb_start_end(uint32_t N, uint32_t n_dub, uint32_t n_tiles_h,
-                                     uint32_t n_tiles_w, const int32_t *aabb_topleft,
-                                     const int32_t *aabb_bottomright, const float *depth,
-                                     int32_t *gaussian_ids, int32_t *start, int32_t *end,
-                                     int64_t *sorted_keys, int check_count, void *scratch,
-                                     size_t scratch_bytes, void *stream) {
-  cudaStream_t st = as_stream(stream);
+// n_dub = capacity of gaussian_ids.  device_count == false: the caller knows the exact count (reference
+// contract).  device_count == true: the count is only known on the device -- duplicate-level kernels are launched
+// for the capacity and bound themselves by the scanned total; nothing is read back.
+static int binning_core(uint32_t N, uint32_t n_dub, uint32_t n_tiles_h, uint32_t n_tiles_w,
+                        const int32_t *aabb_topleft, const int32_t *aabb_bottomright, const float *depth,
+                        int32_t *gaussian_ids, int32_t *start, int32_t *end, int64_t *sorted_keys, int check_count,
+                        bool device_count, int64_t *n_dub_out_dev, int32_t *overflow_dev, void *scratch,
+                        size_t scratch_bytes, cudaStream_t st) {
   const uint32_t n_tiles = n_tiles_h * n_tiles_w;
   GS3D_REQUIRE(start && end && n_tiles > 0, GS3D_EINVAL, "tile_culling_aabb_start_end: bad tiles");
   // aabb_culling.h:248-249
@@ -647,6 +663,8 @@ int gs3d_tile_culling_aabb_start_end(uint32_t N, uint32_t n_dub, uint32_t n_tile
   GS3D_CUDA(cudaMemsetAsync(end, 0xff, sizeof(int32_t) * n_tiles, st));
   if (N == 0) {
     GS3D_REQUIRE(!check_count || n_dub == 0, GS3D_ECOUNT, "n_dub = %u but N = 0", n_dub);
+    if (n_dub_out_dev) GS3D_CUDA(cudaMemsetAsync(n_dub_out_dev, 0, sizeof(int64_t), st));
+    if (overflow_dev) GS3D_CUDA(cudaMemsetAsync(overflow_dev, 0, sizeof(int32_t), st));
     return GS3D_OK;
   }
   GS3D_REQUIRE(aabb_topleft && aabb_bottomright && depth && scratch, GS3D_EINVAL,
@@ -669,11 +687,12 @@ int gs3d_tile_culling_aabb_start_end(uint32_t N, uint32_t n_dub, uint32_t n_tile
   GS3D_REQUIRE(kA && kB && vA && vB && block_sums && rb.table && rb.totals && total &&
                    (n_dub == 0 || (dK0 && dK1 && dV0)),
                GS3D_EINVAL, "tile_culling_aabb_start_end: scratch exhausted");
+  uint32_t *n_eff = device_count ? total + 1 : nullptr;  // min(total, capacity), written by the scan kernel
 
   // 1. depth-byte passes over the Gaussians (low 32 bits of the reference key)
   init_depth_keys_kernel<<<nb256, 256, 0, st>>>(N, depth, kA, vA);
   GS3D_LAUNCH_CHECK();
-  const bool onesweep = use_onesweep();
+  const bool onesweep = use_onesweep() && !device_count;
   if (onesweep) {
     int rc = onesweep_histograms(kA, N, 0, 4, 0, rb, st);
     if (rc) return rc;
@@ -691,9 +710,9 @@ int gs3d_tile_culling_aabb_start_end(uint32_t N, uint32_t n_dub, uint32_t n_tile
   // 2. deterministic offsets: scan of per-Gaussian duplicate counts in depth order
   count_sorted_kernel<<<nb256, 256, 0, st>>>(N, vA, aabb_topleft, aabb_bottomright, block_sums);
   GS3D_LAUNCH_CHECK();
-  scan_block_sums_kernel<<<1, 1024, 0, st>>>(nb256, block_sums, total);
+  scan_block_sums_kernel<<<1, 1024, 0, st>>>(nb256, block_sums, total, n_dub, n_eff, n_dub_out_dev, overflow_dev);
   GS3D_LAUNCH_CHECK();
-  if (check_count) {
+  if (check_count && !device_count) {
     int64_t *box = pinned_mailbox();
     GS3D_REQUIRE(box != nullptr, GS3D_ECUDA, "pinned mailbox unavailable");
     *box = 0;
@@ -714,7 +733,7 @@ int gs3d_tile_culling_aabb_start_end(uint32_t N, uint32_t n_dub, uint32_t n_tile
   uint32_t *vnext = (n_pass & 1) ? ids_u : dV0;
   uint32_t *kcur = dK0, *knext = dK1;
   emit_kernel<<<nb256, 256, 0, st>>>(N, n_dub, n_tiles_w, vA, aabb_topleft, aabb_bottomright,
-                                     block_sums, kcur, vcur);
+                                     block_sums, kcur, vcur, n_eff);
   GS3D_LAUNCH_CHECK();
   if (onesweep && n_pass > 0) {
     int rc = onesweep_histograms(kcur, n_dub, 0, n_pass, 4, rb, st);
@@ -724,20 +743,42 @@ int gs3d_tile_culling_aabb_start_end(uint32_t N, uint32_t n_dub, uint32_t n_tile
     int bits = tile_bits - p * RADIX_BITS;
     if (bits > RADIX_BITS) bits = RADIX_BITS;
     int rc = onesweep ? onesweep_pass(kcur, vcur, knext, vnext, n_dub, p * RADIX_BITS, 4 + p, rb, st)
-                      : radix_pass(kcur, vcur, knext, vnext, n_dub, p * RADIX_BITS, bits, rb, st);
+                      : radix_pass(kcur, vcur, knext, vnext, n_dub, p * RADIX_BITS, bits, rb, st, n_eff);
     if (rc) return rc;
     uint32_t *t = kcur; kcur = knext; knext = t;
     t = vcur; vcur = vnext; vnext = t;
   }
   // 4. tile ranges (+ optional reconstruction of the reference's sorted int64 keys)
   const uint32_t nbd = div_up(n_dub, 256u);
-  ranges_kernel<<<div_up(n_dub, 1024u), 256, 0, st>>>(n_dub, kcur, start, end, n_tiles);
+  ranges_kernel<<<div_up(n_dub, 1024u), 256, 0, st>>>(n_dub, kcur, start, end, n_tiles, n_eff);
   GS3D_LAUNCH_CHECK();
   if (sorted_keys) {
-    keys64_kernel<<<nbd, 256, 0, st>>>(n_dub, kcur, gaussian_ids, depth, sorted_keys);
+    keys64_kernel<<<nbd, 256, 0, st>>>(n_dub, kcur, gaussian_ids, depth, sorted_keys, n_eff);
     GS3D_LAUNCH_CHECK();
   }
   return GS3D_OK;
+}
+
+int gs3d_tile_culling_aabb_start_end(uint32_t N, uint32_t n_dub, uint32_t n_tiles_h,
+                                     uint32_t n_tiles_w, const int32_t *aabb_topleft,
+                                     const int32_t *aabb_bottomright, const float *depth,
+                                     int32_t *gaussian_ids, int32_t *start, int32_t *end,
+                                     int64_t *sorted_keys, int check_count, void *scratch,
+                                     size_t scratch_bytes, void *stream) {
+  return binning_core(N, n_dub, n_tiles_h, n_tiles_w, aabb_topleft, aabb_bottomright, depth, gaussian_ids, start,
+                      end, sorted_keys, check_count, false, nullptr, nullptr, scratch, scratch_bytes,
+                      as_stream(stream));
+}
+
+int gs3d_tile_culling_aabb_start_end_capacity(uint32_t N, uint32_t capacity, uint32_t n_tiles_h,
+                                              uint32_t n_tiles_w, const int32_t *aabb_topleft,
+                                              const int32_t *aabb_bottomright, const float *depth,
+                                              int32_t *gaussian_ids, int32_t *start, int32_t *end,
+                                              int64_t *n_dub_dev, int32_t *overflow_dev, void *scratch,
+                                              size_t scratch_bytes, void *stream) {
+  GS3D_REQUIRE(n_dub_dev && overflow_dev, GS3D_EINVAL, "tile_culling_aabb_start_end_capacity: null count / flag");
+  return binning_core(N, capacity, n_tiles_h, n_tiles_w, aabb_topleft, aabb_bottomright, depth, gaussian_ids, start,
+                      end, nullptr, 0, true, n_dub_dev, overflow_dev, scratch, scratch_bytes, as_stream(stream));
 }
 
 }  // extern "C"

@@ -687,7 +687,7 @@ int gs3d_project_cull_fused(uint32_t N, const float *mean, const float *qvec,
                             float *depth, int32_t *aabb_topleft, int32_t *aabb_bottomright,
                             float *records, float *svec_out, float *alpha_out, int32_t *cnt,
                             int64_t *n_dub_host, void *scratch, size_t scratch_bytes, void *stream) {
-  GS3D_REQUIRE(cam_host && n_dub_host && scratch && scratch_bytes >= 256 && tile_size > 0 && c2w,
+  GS3D_REQUIRE(cam_host && scratch && scratch_bytes >= 256 && tile_size > 0 && c2w,
                GS3D_EINVAL, "gs3d_project_cull_fused: bad argument (scratch must be >= 256 bytes)");
   cudaStream_t st = as_stream(stream);
   unsigned long long *total = static_cast<unsigned long long *>(scratch);
@@ -705,6 +705,7 @@ int gs3d_project_cull_fused(uint32_t N, const float *mean, const float *qvec,
         aabb_topleft, aabb_bottomright, records, svec_out, alpha_out, cnt, total);
     GS3D_LAUNCH_CHECK();
   }
+  if (!n_dub_host) return GS3D_OK;  // no read-back: the count stays in the first 8 bytes of `scratch`
   return read_count(total, n_dub_host, st);
 }
 

@@ -182,8 +182,13 @@ class _splat_sh(torch.autograd.Function):
     (the duplicate count), everything on the current stream."""
 
     @staticmethod
-    def forward(ctx, mean, qvec, svec_param, sh_coeffs, alpha_param, c2w, state):
-        # `state` is a plain dict of Python scalars / tensors / objects prepared by SHRenderer
+    def forward(ctx, mean, qvec, svec_param, sh_coeffs, alpha_param, c2w, state, anchor=None):
+        # `state` is a plain dict of Python scalars / tensors / objects prepared by SHRenderer.
+        # `anchor`: with caller-owned gradient buffers the five parameters arrive DETACHED and this fresh
+        # one-element leaf is the only differentiable input: autograd then just delivers d loss / d image to
+        # backward(), which writes the leaf gradients into the buffers itself.  (Differentiating w.r.t. the
+        # parameters would route through their long-lived AccumulateGrad nodes, whose stream -- the one they were
+        # first used on -- breaks CUDA-graph capture of the step.)
         cam = state["camera_info"]
         tile = state["tile_size"]
         C = state["C"]
@@ -191,21 +196,30 @@ class _splat_sh(torch.autograd.Function):
         mean_c, qvec_c = mean.contiguous(), qvec.contiguous()
         svec_c, alpha_c = svec_param.contiguous(), alpha_param.contiguous()
         c2w_c = c2w.contiguous().float()
+        capacity = state.get("capacity")  # static id-buffer capacity: no host round trip (CUDA-graph capturable)
         k1 = ops.project_cull_fused(
             mean_c, qvec_c, svec_c, alpha_c, state["svec_act"], state["alpha_act"], c2w_c, cam,
             state["frustum_radius"], state["skip_frustum_culling"], state["tile_D"], tile,
-            cnt=state.get("cnt"), want_records=True, want_activated=False)
+            cnt=state.get("cnt"), want_records=True, want_activated=False, sync_count=not capacity)
         H, W = cam.h, cam.w
         nth = H // tile + (H % tile > 0)
         ntw = W // tile + (W % tile > 0)
         n_tiles = nth * ntw
-        n_dub = k1["n_dub"]
-        ids = torch.empty(n_dub, dtype=torch.int32, device=dev)
         start = torch.empty(n_tiles, dtype=torch.int32, device=dev)
         end = torch.empty(n_tiles, dtype=torch.int32, device=dev)
-        ops.tile_culling_aabb_start_end(k1["tl"], k1["br"], ids, start, end, k1["depth"], nth, ntw,
-                                        check_count=False)
-        topleft = torch.tensor([-cam.cx / cam.fx, -cam.cy / cam.fy], dtype=torch.float32).to(dev)
+        if capacity:
+            ids = torch.empty(int(capacity), dtype=torch.int32, device=dev)
+            n_dub, overflow = ops.tile_culling_aabb_start_end_capacity(k1["tl"], k1["br"], ids, start, end,
+                                                                       k1["depth"], nth, ntw)
+            state["overflow"] = overflow
+        else:
+            n_dub = k1["n_dub"]
+            ids = torch.empty(n_dub, dtype=torch.int32, device=dev)
+            ops.tile_culling_aabb_start_end(k1["tl"], k1["br"], ids, start, end, k1["depth"], nth, ntw,
+                                            check_count=False)
+        topleft = state.get("topleft")
+        if topleft is None:
+            topleft = torch.tensor([-cam.cx / cam.fx, -cam.cy / cam.fy], dtype=torch.float32).to(dev)
         psx, psy = 1.0 / cam.fx, 1.0 / cam.fy
         bg = state.get("bg_rgb")
         out = torch.zeros(H * W * 3, dtype=torch.float32, device=dev) if bg is None else \
@@ -237,11 +251,16 @@ class _splat_sh(torch.autograd.Function):
         tile, nth, ntw, psx, psy, H, W, C, thresh, svec_act, alpha_act, detach, exact = ctx.meta
         N = mean.size(0)
         dev = mean.device
-        g_mean2d = torch.zeros(N, 2, dtype=torch.float32, device=dev)
-        g_cov = torch.zeros(N, 4, dtype=torch.float32, device=dev)
-        g_alpha = torch.zeros(N, dtype=torch.float32, device=dev)
         st = ctx.state
         bufs = st.get("grad_buffers")  # caller-owned leaf-gradient buffers (views of a flat buffer)
+        if bufs is not None and bufs.get("g_mean2d") is not None:
+            # persistent 2-D gradient scratch of the owner, cleared row-wise through the `touched` marks together
+            # with the leaf buffers (no 84 MB of fills per backward)
+            g_mean2d, g_cov, g_alpha = bufs["g_mean2d"], bufs["g_cov2d"], bufs["g_alpha2d"]
+        else:
+            g_mean2d = torch.zeros(N, 2, dtype=torch.float32, device=dev)
+            g_cov = torch.zeros(N, 4, dtype=torch.float32, device=dev)
+            g_alpha = torch.zeros(N, dtype=torch.float32, device=dev)
         if bufs is not None:
             g_sh = bufs["sh_coeffs"]  # accumulated into: zeroed by the owner once per step
             leaf_out = (bufs["mean"], bufs["qvec"], bufs["svec_before_activation"],
@@ -270,11 +289,18 @@ class _splat_sh(torch.autograd.Function):
         ref = st.get("mean2d_ref")
         if ref is not None:  # sh_renderer.py:217-221 `mean_2d.retain_grad()` equivalent
             ref.grad = g_mean2d
-        return gm, gq, gs, g_sh, ga, None, None
+        if leaf_out is not None and st.get("anchor") is not None:
+            return None, None, None, None, None, None, None, torch.zeros(1, dtype=torch.float32, device=dev)
+        return gm, gq, gs, g_sh, ga, None, None, None
 
 
 def splat_sh(mean, qvec, svec_param, sh_coeffs, alpha_param, c2w, state):
-    return _splat_sh.apply(mean, qvec, svec_param, sh_coeffs, alpha_param, c2w, state)
+    if state.get("grad_buffers") is not None and torch.is_grad_enabled():
+        anchor = torch.zeros(1, dtype=torch.float32, device=mean.device, requires_grad=True)
+        state["anchor"] = anchor
+        return _splat_sh.apply(mean.detach(), qvec.detach(), svec_param.detach(), sh_coeffs.detach(),
+                               alpha_param.detach(), c2w, state, anchor)
+    return _splat_sh.apply(mean, qvec, svec_param, sh_coeffs, alpha_param, c2w, state, None)
 
 
 def _legacy(name):

@@ -85,6 +85,13 @@ class SHRenderer(torch.nn.Module):
         self.depth = None
         self.radius = None
         self.total_dub_gaussians = 0
+        # Opt-in: a fixed capacity (in duplicates) for the tile lists.  The forward then never reads the duplicate
+        # count back (the reference's `.item()`, gs/culling.py:33-35): no host sync, every launch sized by the
+        # capacity, so a whole training step can be captured in a CUDA graph (graph.GraphedStep).  When the
+        # count exceeds the capacity the lists are truncated and `overflowed()` reports it.
+        self.static_capacity = None
+        self._overflow = None
+        self._topleft_cache = {}
         self.fuse_adc = False  # accumulate grad_mean inside the backward kernel (see update_grads)
         # Optional caller-owned leaf-gradient buffers {param name: tensor}: backward ADDS into them
         # instead of allocating (parallel.FlatGradients); use torch.autograd.grad, not .backward().
@@ -189,12 +196,14 @@ class SHRenderer(torch.nn.Module):
             "bg_rgb": self.bg_rgb if self.bg else None, "exact": self.exact_decisions,
             "adc_acc": self.grad_mean if adc_mode else None, "adc_mode": adc_mode,
             "grad_buffers": self.grad_buffers,
+            "capacity": self.static_capacity, "topleft": self._topleft(camera_info),
         }
         out = splat_sh(self.mean, self.qvec, self.svec_before_activation, self.sh_coeffs,
                        self.alpha_before_activation, c2w, state)
         k1 = state.pop("out_k1")
         self._state = state
-        self.total_dub_gaussians = state["n_dub"]
+        self.total_dub_gaussians = state["n_dub"]  # int, or an int64 [1] device tensor in static-capacity mode
+        self._overflow = state.get("overflow")
         self.depth = k1["depth"]
         self.radius = None
         if training_2d:
@@ -202,6 +211,32 @@ class SHRenderer(torch.nn.Module):
             self.mean_2d = k1["mean2d"]
             state["mean2d_ref"] = self.mean_2d  # backward sets .grad on it
         return out.view(camera_info.h, camera_info.w, 3)
+
+    def _topleft(self, cam):
+        """(-cx/fx, -cy/fy) on the device, uploaded once per camera instead of once per frame."""
+        key = (float(cam.fx), float(cam.fy), float(cam.cx), float(cam.cy), str(self.mean.device))
+        t = self._topleft_cache.get(key)
+        if t is None:
+            t = torch.tensor([-cam.cx / cam.fx, -cam.cy / cam.fy], dtype=torch.float32).to(self.mean.device)
+            if len(self._topleft_cache) > 64:
+                self._topleft_cache.clear()
+            self._topleft_cache[key] = t
+        return t
+
+    @property
+    def total_dub_gaussians(self):
+        """Duplicate count of the last forward (a Python int like the reference's; in static-capacity mode the
+        count lives on the device and reading it here synchronises)."""
+        v = self._n_dub
+        return int(v.item()) if isinstance(v, torch.Tensor) else v
+
+    @total_dub_gaussians.setter
+    def total_dub_gaussians(self, v):
+        self._n_dub = v
+
+    def overflowed(self):
+        """static-capacity mode: did the last forward need more duplicates than `static_capacity`?  (syncs)"""
+        return bool(self._overflow is not None and int(self._overflow.item()) != 0)
 
     @property
     def svec(self):

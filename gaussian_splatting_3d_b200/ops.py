@@ -112,7 +112,9 @@ def tile_culling_aabb_count(mean2d, cov, tile_size, camera_info, D):
 # ---------------------------------------------------------------- fused K1
 def project_cull_fused(mean, qvec, svec_param, alpha_param, svec_act, alpha_act, c2w, camera_info,
                        frustum_radius, skip_frustum_culling, tile_D, tile_size, cnt=None,
-                       want_records=True, want_activated=True):
+                       want_records=True, want_activated=True, sync_count=True):
+    """sync_count=False: no host read-back of the duplicate count (out["n_dub"] is None, out["n_dub_dev"] an
+    int64 [1] device view of it): the call, and the step around it, can be captured in a CUDA graph."""
     for t, n in ((mean, "mean"), (qvec, "qvec"), (svec_param, "svec"), (alpha_param, "alpha"),
                  (c2w, "c2w")):
         _chk(t, n, _F32)
@@ -134,14 +136,16 @@ def project_cull_fused(mean, qvec, svec_param, alpha_param, svec_act, alpha_act,
     n = C.c_int64(0)
     scratch = _scratch(256, dev)
     cam = capi.camera_struct(camera_info)
+    n_arg = C.cast(C.pointer(n), C.c_void_p) if sync_count else None
     check(capi.lib.gs3d_project_cull_fused(
         N, ptr(mean), ptr(qvec), ptr(svec_param), ptr(alpha_param), int(svec_act), int(alpha_act),
         ptr(c2w), C.byref(cam), float(frustum_radius), 1 if skip_frustum_culling else 0,
         float(tile_D), int(tile_size), ptr(out["mask"]), ptr(out["mean2d"]), ptr(out["cov"]),
         ptr(out["depth"]), ptr(out["tl"]), ptr(out["br"]), ptr(out["records"]), ptr(out["svec"]),
-        ptr(out["alpha"]), ptr(cnt), C.byref(n), ptr(scratch), scratch.numel(), _stream(mean)),
+        ptr(out["alpha"]), ptr(cnt), n_arg, ptr(scratch), scratch.numel(), _stream(mean)),
         "project_cull_fused")
-    out["n_dub"] = int(n.value)
+    out["n_dub"] = int(n.value) if sync_count else None
+    out["n_dub_dev"] = scratch[:8].view(_I64)
     return out
 
 
@@ -165,6 +169,30 @@ def tile_culling_aabb_start_end(aabb_topleft, aabb_bottomright, gaussian_ids, st
         ptr(depth), ptr(gaussian_ids), ptr(start), ptr(end), ptr(sorted_keys),
         1 if check_count else 0, ptr(scratch), scratch.numel(), _stream(depth)),
         "tile_culling_aabb_start_end")
+
+
+def tile_culling_aabb_start_end_capacity(aabb_topleft, aabb_bottomright, gaussian_ids, start, end, depth,
+                                         n_tiles_h, n_tiles_w):
+    """Binning without a host round trip: gaussian_ids is a buffer of CAPACITY entries.  -> (n_dub int64 [1],
+    overflow int32 [1]) device tensors; overflow != 0 means the capacity was too small and the lists are
+    truncated (see gs3d_tile_culling_aabb_start_end_capacity)."""
+    for t, n in ((aabb_topleft, "aabb_topleft"), (aabb_bottomright, "aabb_bottomright"),
+                 (gaussian_ids, "gaussian_ids"), (start, "start"), (end, "end")):
+        _chk(t, n, _I32)
+    _chk(depth, "depth", _F32)
+    N = aabb_topleft.size(0)
+    cap = gaussian_ids.size(0)
+    if start.numel() < n_tiles_h * n_tiles_w or end.numel() < n_tiles_h * n_tiles_w:
+        raise RuntimeError("start/end must have n_tiles_h * n_tiles_w elements")
+    dev = depth.device
+    n_dub = torch.empty(1, dtype=_I64, device=dev)
+    overflow = torch.empty(1, dtype=_I32, device=dev)
+    scratch = _scratch(capi.lib.gs3d_binning_scratch_bytes(N, cap), dev)
+    check(capi.lib.gs3d_tile_culling_aabb_start_end_capacity(
+        N, cap, int(n_tiles_h), int(n_tiles_w), ptr(aabb_topleft), ptr(aabb_bottomright), ptr(depth),
+        ptr(gaussian_ids), ptr(start), ptr(end), ptr(n_dub), ptr(overflow), ptr(scratch), scratch.numel(),
+        _stream(depth)), "tile_culling_aabb_start_end_capacity")
+    return n_dub, overflow
 
 
 # ---------------------------------------------------------------- records

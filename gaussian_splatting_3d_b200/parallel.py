@@ -75,6 +75,11 @@ class FlatGradients:
         self.sparse_reset = bool(sparse_reset) and not self.fused and not self.push and dev.type == "cuda"
         self.touched = (torch.zeros(N, dtype=torch.uint8, device=dev)
                         if (self.sparse or self.push or self.sparse_reset) else None)
+        # persistent 2-D gradient scratch (d loss / d mean2d, cov2d, alpha of the compositing backward): cleared
+        # through the same marks as the leaf rows instead of three full-size fills per backward
+        self.g2d = ([torch.zeros(N, 2, dtype=torch.float32, device=dev), torch.zeros(N, 4, dtype=torch.float32, device=dev),
+                     torch.zeros(N, dtype=torch.float32, device=dev)]
+                    if (self.touched is not None and not self.sparse and dev.type == "cuda") else None)
         self.last_union_rows = None
         self.handle = None
         self.local = self.local_views = self.union = self.union_handle = None
@@ -172,6 +177,8 @@ class FlatGradients:
             bufs["sh_multicast_ptr"] = self.multicast_ptr
         if self.touched is not None:
             bufs["touched"] = self.touched
+        if self.g2d is not None:
+            bufs["g_mean2d"], bufs["g_cov2d"], bufs["g_alpha2d"] = self.g2d
         renderer.grad_buffers = bufs
         self.module = renderer
         return self
@@ -207,7 +214,7 @@ class FlatGradients:
             cur, nxt = self._res[self._cur], self._res[self._cur ^ 1]
 
             def resets():
-                ops.rows_zero_marked(self.touched, self.local_views, clear_marks=True)
+                ops.rows_zero_marked(self.touched, list(self.local_views) + (self.g2d or []), clear_marks=True)
                 ops.rows_zero_marked(nxt["union"], nxt["views"], clear_marks=True)
 
             if self._aux is not None:
@@ -219,7 +226,7 @@ class FlatGradients:
         elif self.sparse_reset and self.module is not None:
             from . import ops
 
-            ops.rows_zero_marked(self.touched, self.views, clear_marks=True)
+            ops.rows_zero_marked(self.touched, list(self.views) + (self.g2d or []), clear_marks=True)
         else:
             self.flat.zero_()
             if self.touched is not None:
@@ -238,7 +245,10 @@ class FlatGradients:
         if self.module is None:
             loss.backward()  # plain autograd accumulation into the aliased .grad views
         else:
-            torch.autograd.grad(loss, self.params)
+            # the attached renderer's forward made a fresh one-element leaf its only differentiable input
+            # (gs/renderer.py splat_sh): backward() writes the leaf gradients into this object's buffers itself
+            anchor = (self.module._state or {}).get("anchor") if hasattr(self.module, "_state") else None
+            torch.autograd.grad(loss, [anchor] if anchor is not None else self.params)
 
     def exchange(self, average=False):
         """Make every rank's buffer hold the sum over ranks."""

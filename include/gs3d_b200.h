@@ -100,7 +100,9 @@ int gs3d_tile_culling_aabb_count(uint32_t N, const float *mean2d, const float *c
  * Outputs: mask [N] u8, mean2d [N,2], cov2d [N,4], depth [N], aabb tl/br int32 [N,2],
  * records [N,12] (may be NULL), svec_out [N,3] / alpha_out [N] activated values (may be NULL),
  * cnt int32 [N] (may be NULL): cnt[i] += 1 for kept Gaussians (sh_renderer.py:215-216).
- * *n_dub_host is valid after return (one 8-byte D2H + stream sync). */
+ * *n_dub_host is valid after return (one 8-byte D2H + stream sync).  n_dub_host == NULL: no read-back and no
+ * synchronisation -- the count stays on the device in the first 8 bytes of `scratch` (uint64); use it with
+ * gs3d_tile_culling_aabb_start_end_capacity. */
 int gs3d_project_cull_fused(uint32_t N, const float *mean, const float *qvec,
                             const float *svec_param, const float *alpha_param, int svec_act,
                             int alpha_act, const float *c2w, const gs3d_camera *cam_host,
@@ -126,6 +128,21 @@ int gs3d_tile_culling_aabb_start_end(uint32_t N, uint32_t n_dub, uint32_t n_tile
                                      int32_t *gaussian_ids, int32_t *start, int32_t *end,
                                      int64_t *sorted_keys, int check_count, void *scratch,
                                      size_t scratch_bytes, void *stream);
+
+/* Same binning without ANY host round trip: the reference learns the duplicate count through `.item()`
+ * (gs/culling.py:33-35) and a D2H memcpy (aabb_culling.h:222-228) before it can size gaussian_ids.  Here the
+ * caller passes a buffer of `capacity` ids instead; the count only ever exists on the device: n_dub_dev
+ * (int64, device) receives the true count, overflow_dev (int32, device) is set to 1 when it exceeded the
+ * capacity -- the lists are then truncated (the farthest duplicates are dropped) and the caller must re-run with
+ * a larger buffer.  Every launch is sized by the capacity, so the call (and with gs3d_project_cull_fused's
+ * n_dub_host == NULL the whole forward+backward step) can be captured in a CUDA graph.
+ * Scratch: gs3d_binning_scratch_bytes(N, capacity). */
+int gs3d_tile_culling_aabb_start_end_capacity(uint32_t N, uint32_t capacity, uint32_t n_tiles_h,
+                                              uint32_t n_tiles_w, const int32_t *aabb_topleft,
+                                              const int32_t *aabb_bottomright, const float *depth,
+                                              int32_t *gaussian_ids, int32_t *start, int32_t *end,
+                                              int64_t *n_dub_dev, int32_t *overflow_dev, void *scratch,
+                                              size_t scratch_bytes, void *stream);
 
 /* ---- staging records from raw arrays (used by the reference-signature wrappers below). */
 int gs3d_pack_records(uint32_t N, const float *mean2d, const float *cov2d, const float *alpha,

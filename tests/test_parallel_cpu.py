@@ -101,8 +101,12 @@ def test_view_sharded_gradient_allreduce_gloo_world2():
     ps = [torch.randn(n, 3, generator=g), torch.randn(n, 4, generator=g), torch.randn(n, 3, generator=g),
           torch.randn(n, 3, 4, generator=g), torch.randn(n, generator=g)]
     scale = sum(2.0 * (v + 1) ** 2 for v in range(8))
-    # flat layout: [sh_coeffs | mean | qvec | svec | alpha]
-    want = torch.cat([(p * scale).reshape(-1) for p in (ps[3], ps[0], ps[1], ps[2], ps[4])])
+    # flat layout: [sh_coeffs | mean | qvec | svec | alpha], every block padded to a multiple of 4 floats (16 bytes)
+    def padded(t):
+        v = (t * scale).reshape(-1)
+        return torch.cat([v, torch.zeros((-v.numel()) % 4)])
+
+    want = torch.cat([padded(p) for p in (ps[3], ps[0], ps[1], ps[2], ps[4])])
     assert torch.allclose(f0, want, rtol=1e-5, atol=1e-5)
     assert torch.equal(gm0, gm1) and float(gm0[0]) == float(sum(range(1, 9)))
     assert torch.equal(c0, c1) and int(c0[0]) == 8
