@@ -376,14 +376,21 @@ project_cull_fused_kernel(uint32_t N, const float *__restrict__ mean,
   if (threadIdx.x < 12) c2w[threadIdx.x] = c2w_g[threadIdx.x];
   else if (threadIdx.x >= 32 && threadIdx.x < 68) planes[threadIdx.x - 32] = planes_g[threadIdx.x - 32];
   __syncthreads();
+  // staging records leave through shared memory: the 256 records of a block are 12 KB of CONTIGUOUS global
+  // memory, written as full 16-byte-per-lane coalesced rows instead of three 48-byte-strided stores per thread
+  __shared__ float4 s_rec[256 * 3];
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   unsigned long long n_dup = 0;
+  float4 rec[3] = {make_float4(0.f, 0.f, 0.f, INFINITY), make_float4(0.f, 0.f, 0.f, 0.f),
+                   make_float4(1.f, 0.f, 0.f, 1.f)};  // culled: never contributes
   if (i < N) {
-    float p[3] = {mean[3 * (size_t)i], mean[3 * (size_t)i + 1], mean[3 * (size_t)i + 2]};
-    float s[3] = {act_exp(svec_param[3 * (size_t)i], svec_act),
-                  act_exp(svec_param[3 * (size_t)i + 1], svec_act),
-                  act_exp(svec_param[3 * (size_t)i + 2], svec_act)};
-    float a = act_sigmoid(alpha_param[i], alpha_act);
+    // every load is issued before the first use (one memory round trip, the cull test included)
+    const float p[3] = {mean[3 * (size_t)i], mean[3 * (size_t)i + 1], mean[3 * (size_t)i + 2]};
+    const float sp[3] = {svec_param[3 * (size_t)i], svec_param[3 * (size_t)i + 1], svec_param[3 * (size_t)i + 2]};
+    const float ap = alpha_param[i];
+    const float4 q4 = reinterpret_cast<const float4 *>(qvec)[i];
+    float s[3] = {act_exp(sp[0], svec_act), act_exp(sp[1], svec_act), act_exp(sp[2], svec_act)};
+    float a = act_sigmoid(ap, alpha_act);
     if (svec_out) {
       svec_out[3 * (size_t)i] = s[0];
       svec_out[3 * (size_t)i + 1] = s[1];
@@ -401,7 +408,6 @@ project_cull_fused_kernel(uint32_t N, const float *__restrict__ mean,
     float4 cv = make_float4(0.f, 0.f, 0.f, 0.f);
     float dz = 0.f;
     if (keep) {
-      float4 q4 = reinterpret_cast<const float4 *>(qvec)[i];
       float q[4] = {q4.x, q4.y, q4.z, q4.w};
       Projected o;
       project_one(p, q, s, c2w, o);
@@ -413,20 +419,27 @@ project_cull_fused_kernel(uint32_t N, const float *__restrict__ mean,
       long long pr = w * h;
       n_dup = pr > 0 ? (unsigned long long)pr : 0ull;
       if (cnt) cnt[i] += 1;  // sh_renderer.py:215-216
+      if (records) make_record(m2.x, m2.y, cv.x, cv.y, cv.z, cv.w, a, dz, rec);
     }
-    reinterpret_cast<float2 *>(mean2d)[i] = m2;
-    reinterpret_cast<float4 *>(cov2d)[i] = cv;
+    // mean2d / cov2d are optional: the staging record already holds both (floats 0-1 and 8-11)
+    if (mean2d) reinterpret_cast<float2 *>(mean2d)[i] = m2;
+    if (cov2d) reinterpret_cast<float4 *>(cov2d)[i] = cv;
     depth[i] = dz;
     reinterpret_cast<int2 *>(tl)[i] = make_int2(rc.tlx, rc.tly);
     reinterpret_cast<int2 *>(br)[i] = make_int2(rc.brx, rc.bry);
-    if (records) {
-      float4 *rec = reinterpret_cast<float4 *>(records) + 3 * (size_t)i;
-      if (keep) make_record(m2.x, m2.y, cv.x, cv.y, cv.z, cv.w, a, dz, rec);
-      else {
-        rec[0] = make_float4(0.f, 0.f, 0.f, INFINITY);
-        rec[1] = make_float4(0.f, 0.f, 0.f, 0.f);
-        rec[2] = make_float4(1.f, 0.f, 0.f, 1.f);
-      }
+  }
+  if (records) {
+    s_rec[3 * threadIdx.x + 0] = rec[0];
+    s_rec[3 * threadIdx.x + 1] = rec[1];
+    s_rec[3 * threadIdx.x + 2] = rec[2];
+    __syncthreads();
+    const size_t base4 = (size_t)blockIdx.x * (256 * 3);  // float4 index of the block's first record
+    const size_t end4 = (size_t)N * 3;
+    float4 *out4 = reinterpret_cast<float4 *>(records);
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+      const size_t e = base4 + r * 256 + threadIdx.x;
+      if (e < end4) out4[e] = s_rec[r * 256 + threadIdx.x];
     }
   }
   block_count_add(n_dup, total);
@@ -693,9 +706,10 @@ int gs3d_project_cull_fused(uint32_t N, const float *mean, const float *qvec,
   unsigned long long *total = static_cast<unsigned long long *>(scratch);
   GS3D_CUDA(cudaMemsetAsync(total, 0, 8, st));
   if (N) {
-    GS3D_REQUIRE(mean && qvec && svec_param && alpha_param && mask && mean2d && cov2d && depth &&
-                     aabb_topleft && aabb_bottomright,
+    GS3D_REQUIRE(mean && qvec && svec_param && alpha_param && mask && depth && aabb_topleft && aabb_bottomright,
                  GS3D_EINVAL, "gs3d_project_cull_fused: null argument");
+    GS3D_REQUIRE((mean2d && cov2d) || records, GS3D_EINVAL,
+                 "gs3d_project_cull_fused: mean2d / cov2d may only be NULL when records are written");
     float *planes = reinterpret_cast<float *>(static_cast<char *>(scratch) + 64);  // 36 floats
     frustum_kernel<<<1, 32, 0, st>>>(c2w, make_cam(cam_host), planes, planes + 18);
     GS3D_LAUNCH_CHECK();

@@ -200,7 +200,8 @@ class _splat_sh(torch.autograd.Function):
         k1 = ops.project_cull_fused(
             mean_c, qvec_c, svec_c, alpha_c, state["svec_act"], state["alpha_act"], c2w_c, cam,
             state["frustum_radius"], state["skip_frustum_culling"], state["tile_D"], tile,
-            cnt=state.get("cnt"), want_records=True, want_activated=False, sync_count=not capacity)
+            cnt=state.get("cnt"), want_records=True, want_activated=False, sync_count=not capacity,
+            want_projection=False)
         H, W = cam.h, cam.w
         nth = H // tile + (H % tile > 0)
         ntw = W // tile + (W % tile > 0)

@@ -32,8 +32,24 @@ def _stream(t):
     return capi.current_stream(t.device)
 
 
+_SCRATCH = {}  # (device, stream) -> persistent uint8 buffer, grown on demand
+
+
 def _scratch(nbytes, device):
-    return torch.empty(max(int(nbytes), 256), dtype=_U8, device=device)
+    """Kernel scratch.  Large requests (the binning's ping-pong buffers, ~200 MB at cfg 2) are served from one
+    persistent buffer per (device, stream) -- consecutive calls on a stream are ordered, so they can share it --
+    instead of a fresh caching-allocator block per call.  During CUDA-graph capture the buffer comes from the
+    graph's own pool (it must stay alive with the graph, not with this cache)."""
+    nbytes = max(int(nbytes), 256)
+    if nbytes < (1 << 20) or torch.cuda.is_current_stream_capturing():
+        return torch.empty(nbytes, dtype=_U8, device=device)
+    device = torch.device(device)
+    key = (device.index if device.index is not None else torch.cuda.current_device(),
+           torch.cuda.current_stream(device).cuda_stream)
+    buf = _SCRATCH.get(key)
+    if buf is None or buf.numel() < nbytes:
+        _SCRATCH[key] = buf = torch.empty(nbytes + nbytes // 8, dtype=_U8, device=device)
+    return buf
 
 
 # ---------------------------------------------------------------- a1
@@ -112,20 +128,24 @@ def tile_culling_aabb_count(mean2d, cov, tile_size, camera_info, D):
 # ---------------------------------------------------------------- fused K1
 def project_cull_fused(mean, qvec, svec_param, alpha_param, svec_act, alpha_act, c2w, camera_info,
                        frustum_radius, skip_frustum_culling, tile_D, tile_size, cnt=None,
-                       want_records=True, want_activated=True, sync_count=True):
+                       want_records=True, want_activated=True, sync_count=True, want_projection=True):
     """sync_count=False: no host read-back of the duplicate count (out["n_dub"] is None, out["n_dub_dev"] an
-    int64 [1] device view of it): the call, and the step around it, can be captured in a CUDA graph."""
+    int64 [1] device view of it): the call, and the step around it, can be captured in a CUDA graph.
+    want_projection=False (needs want_records): mean2d / cov are not written as separate arrays; out["mean2d"]
+    and out["cov"] are then strided VIEWS into the staging records (floats 0-1 and 8-11)."""
     for t, n in ((mean, "mean"), (qvec, "qvec"), (svec_param, "svec"), (alpha_param, "alpha"),
                  (c2w, "c2w")):
         _chk(t, n, _F32)
     if cnt is not None:
         _chk(cnt, "cnt", _I32)
+    if not want_projection and not want_records:
+        raise RuntimeError("want_projection=False needs want_records=True")
     N = mean.size(0)
     dev = mean.device
     out = {
         "mask": torch.empty(N, dtype=_BOOL, device=dev),
-        "mean2d": torch.empty(N, 2, dtype=_F32, device=dev),
-        "cov": torch.empty(N, 2, 2, dtype=_F32, device=dev),
+        "mean2d": torch.empty(N, 2, dtype=_F32, device=dev) if want_projection else None,
+        "cov": torch.empty(N, 2, 2, dtype=_F32, device=dev) if want_projection else None,
         "depth": torch.empty(N, 1, dtype=_F32, device=dev),
         "tl": torch.empty(N, 2, dtype=_I32, device=dev),
         "br": torch.empty(N, 2, dtype=_I32, device=dev),
@@ -146,6 +166,9 @@ def project_cull_fused(mean, qvec, svec_param, alpha_param, svec_act, alpha_act,
         "project_cull_fused")
     out["n_dub"] = int(n.value) if sync_count else None
     out["n_dub_dev"] = scratch[:8].view(_I64)
+    if not want_projection:
+        out["mean2d"] = out["records"][:, 0:2]
+        out["cov"] = out["records"][:, 8:12]
     return out
 
 

@@ -99,6 +99,8 @@ int gs3d_tile_culling_aabb_count(uint32_t N, const float *mean2d, const float *c
  * and mask 0; nothing is compacted, ids stay original indices.
  * Outputs: mask [N] u8, mean2d [N,2], cov2d [N,4], depth [N], aabb tl/br int32 [N,2],
  * records [N,12] (may be NULL), svec_out [N,3] / alpha_out [N] activated values (may be NULL),
+ * mean2d and cov2d may BOTH be NULL when records is not: the record already holds them (floats 0-1 = mean2d,
+ * floats 8-11 = cov2d; for a culled Gaussian the record's covariance is the identity, not zero),
  * cnt int32 [N] (may be NULL): cnt[i] += 1 for kept Gaussians (sh_renderer.py:215-216).
  * *n_dub_host is valid after return (one 8-byte D2H + stream sync).  n_dub_host == NULL: no read-back and no
  * synchronisation -- the count stays on the device in the first 8 bytes of `scratch` (uint64); use it with

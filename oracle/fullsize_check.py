@@ -16,6 +16,10 @@ Reported per workload (all counts are over the whole scene, nothing sampled):
   keys_equal           sorted (tile, depth-bits) key sequence identical (ids may differ inside ties)
   ids_tie_only         ids identical up to the order inside equal-key runs
   image_max_abs / image_gt_1e4   max |ours - ref| and the number of image elements above 1e-4
+  image_*_raw, image_gt_1e4_outside_tie_tiles, tie_tiles   only when the reference's order inside equal-key runs
+                       (unspecified: its emission uses atomics, aabb_culling.h:26-38) differs from ours in a tile
+                       whose pixels then differ: `*_raw` keep the direct comparison, the headline numbers are
+                       this repo's compositing kernel run on the REFERENCE's id order (same records, same ranges)
   grad_<leaf>_{l2,max} relative L2 / max-abs-over-max error of every leaf gradient (L2 loss)
 """
 import contextlib
@@ -159,6 +163,36 @@ def compare_whole_path(ext, name, N=None, seed=0, backward=True, device="cuda:0"
     res["image_max_abs"] = float(err.max())
     res["image_gt_1e4"] = int((err > 1e-4).sum())
     res["image_elems"] = int(err.numel())
+    if res["image_gt_1e4"] and res.get("ids_differ", 0) and res["keys_equal"] and res["ids_tie_only"]:
+        # Two Gaussians with the same depth bits in one tile: the reference emits them in whatever order its
+        # atomicAdd hands out (run to run), this repo in ascending id.  When such a pair is near the front of a
+        # tile the blend order moves a few pixels by ~1e-3.  Attribute the offending pixels to tiles whose lists
+        # differ, then composite the REFERENCE's order with this repo's kernel: that must match everywhere.
+        H, W, tile = cam.h, cam.w, 16
+        nth, ntw = (H + tile - 1) // tile, (W + tile - 1) // tile
+        pos = torch.nonzero(ids_o != ref_keep["ids"]).view(-1)
+        tile_of = torch.searchsorted(e_o.clamp_min(0).cummax(0).values.long(), pos, right=True)  # ends ascend over non-empty tiles
+        tie_tiles = torch.zeros(nth * ntw, dtype=torch.bool, device=dev)
+        tie_tiles[tile_of.clamp_max(nth * ntw - 1)] = True
+        bad = (err.reshape(H, W, 3) > 1e-4).any(dim=2)
+        ys, xs = torch.nonzero(bad, as_tuple=True)
+        in_tie = tie_tiles[(ys // tile) * ntw + (xs // tile)]
+        res["tie_tiles"] = int(tie_tiles.sum())
+        res["image_gt_1e4_outside_tie_tiles"] = int((~in_tie).sum())
+        res["image_max_abs_raw"], res["image_gt_1e4_raw"] = res["image_max_abs"], res["image_gt_1e4"]
+        k1r = ops.project_cull_fused(r.mean.data, r.qvec.data, r.svec_before_activation.data,
+                                     r.alpha_before_activation.data, 1, 1, c2w, cam, 1.0, False, 6.0, 16,
+                                     want_records=True, want_activated=False)
+        out2 = torch.zeros(H * W * 3, dtype=torch.float32, device=dev)
+        topleft = torch.tensor([-cam.cx / cam.fx, -cam.cy / cam.fy], dtype=torch.float32, device=dev)
+        ops.composite_sh_forward(k1r["records"], r.sh_coeffs.data[:, :, :C * C].contiguous(), s_o, e_o,
+                                 ref_keep["ids"].contiguous(), out2, topleft, c2w, tile, nth, ntw, 1.0 / cam.fx,
+                                 1.0 / cam.fy, H, W, C, 1e-4, bg_rgb=bg_t, exact=True)
+        err2 = (out2.view_as(ref_keep["out"]) - ref_keep["out"]).abs()
+        if res["image_gt_1e4_outside_tie_tiles"] == 0:
+            res["image_max_abs"] = float(err2.max())
+            res["image_gt_1e4"] = int((err2 > 1e-4).sum())
+        del k1r, out2, err2
     if backward:
         for k in ("mean", "qvec", "svec_before_activation", "sh_coeffs", "alpha_before_activation"):
             got, want = getattr(r, k).grad, ref_grads[k]
@@ -173,7 +207,8 @@ def compare_whole_path(ext, name, N=None, seed=0, backward=True, device="cuda:0"
 
 def summarize(res):
     keys = ("workload", "N", "n_dub_ours", "n_dub_ref", "mask_mismatch", "bits_svec", "bits_alpha", "bits_mean2d", "bits_cov", "bits_depth",
-            "rect_mismatch", "ranges_equal", "keys_equal", "ids_tie_only", "image_max_abs", "image_gt_1e4")
+            "rect_mismatch", "ranges_equal", "keys_equal", "ids_tie_only", "image_max_abs", "image_gt_1e4",
+            "image_max_abs_raw", "image_gt_1e4_raw", "tie_tiles", "image_gt_1e4_outside_tie_tiles")
     s = ", ".join(f"{k}={res[k]}" for k in keys if k in res)
     g = ", ".join(f"{k[5:]}={res[k]:.2e}" for k in sorted(res) if k.startswith("grad_"))
     return s + (("; grads: " + g) if g else "")
@@ -182,7 +217,8 @@ def summarize(res):
 def passes(res, image_tol=1e-4, grad_tol=1e-3):
     """The north-star bars: bit-exact binning, image <= 1e-4 max-abs, gradients <= 1e-3 relative."""
     ok = (res["n_dub_ours"] == res["n_dub_ref"] and res["mask_mismatch"] == 0 and res["rect_mismatch"] == 0
-          and res["ranges_equal"] and res["keys_equal"] and res["ids_tie_only"] and res["image_max_abs"] <= image_tol)
+          and res["ranges_equal"] and res["keys_equal"] and res["ids_tie_only"] and res["image_max_abs"] <= image_tol
+          and res.get("image_gt_1e4_outside_tie_tiles", 0) == 0)
     for k, v in res.items():
         if k.startswith("grad_") and k.endswith("_l2"):
             ok = ok and v <= grad_tol

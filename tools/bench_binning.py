@@ -34,10 +34,14 @@ print('binning ms', e0.elapsed_time(e1) / 20, 'n_dub', n)
 if '--save' in sys.argv:
     path = sys.argv[sys.argv.index('--save') + 1]
     torch.save({'ids': ids.cpu(), 'start': st.cpu(), 'end': en.cpu()}, path)
+def k1fast():
+    return ops.project_cull_fused(sc_d['mean'], sc_d['qvec'], sc_d['svec_before_activation'],
+                                  sc_d['alpha_before_activation'], 1, 1, sc_d['c2w'], cam, 1.0, False, 6.0, 16,
+                                  want_activated=False, want_projection=False, sync_count=False)
 if '--kernels' in sys.argv:
     from torch.profiler import profile, ProfilerActivity
     with profile(activities=[ProfilerActivity.CUDA]) as prof:
-        for _ in range(5): run()
+        for _ in range(5): run(); k1fast()
         torch.cuda.synchronize()
     agg = collections.OrderedDict()
     for ev in prof.events():
@@ -49,8 +53,9 @@ if '--kernels' in sys.argv:
     for k, (c, t) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
         print(f'{t / 5:9.1f} us/call {c // 5:3d}x  {k}')
     print(f'{tot / 5:9.1f} us/call total kernel time')
-for _ in range(3): k1run()
-torch.cuda.synchronize(); e0.record()
-for _ in range(20): k1run()
-e1.record(); torch.cuda.synchronize()
-print('K1 ms', e0.elapsed_time(e1) / 20)
+for f, nm in ((k1run, 'K1 (all outputs, count read back)'), (k1fast, 'K1 (product path: records only, no sync)')):
+    for _ in range(3): f()
+    torch.cuda.synchronize(); e0.record()
+    for _ in range(20): f()
+    e1.record(); torch.cuda.synchronize()
+    print(nm, 'ms', e0.elapsed_time(e1) / 20)
