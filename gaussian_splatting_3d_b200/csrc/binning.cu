@@ -26,20 +26,22 @@ constexpr int SORT_WARPS = SORT_THREADS / 32;
 
 // ---------------------------------------------------------------- radix pass
 
+template <int IPT = SORT_IPT>
 __global__ void __launch_bounds__(SORT_THREADS)
 radix_hist_kernel(const uint32_t *__restrict__ keys, uint32_t n, int shift, uint32_t mask,
                   uint32_t nblocks, uint32_t *__restrict__ table /*[RADIX][nblocks]*/,
                   uint32_t *__restrict__ totals /*[RADIX]*/, const uint32_t *__restrict__ n_dev) {
+  constexpr int TILE_ITEMS = SORT_THREADS * IPT;  // must match the scatter kernel's tile
   __shared__ uint32_t h[RADIX];
   if (n_dev) n = min(n, *n_dev);  // capacity-sized launch: the real item count lives on the device
   h[threadIdx.x] = 0;
   __syncthreads();
-  size_t base = (size_t)blockIdx.x * SORT_TILE;
-  if (base + SORT_TILE <= n && (reinterpret_cast<uintptr_t>(keys) & 15) == 0) {
+  size_t base = (size_t)blockIdx.x * TILE_ITEMS;
+  if (base + TILE_ITEMS <= n && (reinterpret_cast<uintptr_t>(keys) & 15) == 0) {
     // full tile: 16-byte loads (a histogram does not care which thread counts which key)
     const uint4 *k4 = reinterpret_cast<const uint4 *>(keys + base);
 #pragma unroll
-    for (int i = 0; i < SORT_IPT / 4; ++i) {
+    for (int i = 0; i < IPT / 4; ++i) {
       const uint4 v = k4[i * SORT_THREADS + threadIdx.x];
       atomicAdd(&h[(v.x >> shift) & mask], 1u);
       atomicAdd(&h[(v.y >> shift) & mask], 1u);
@@ -48,7 +50,7 @@ radix_hist_kernel(const uint32_t *__restrict__ keys, uint32_t n, int shift, uint
     }
   } else {
 #pragma unroll 4
-    for (int i = 0; i < SORT_IPT; ++i) {
+    for (int i = 0; i < IPT; ++i) {
       size_t e = base + (size_t)i * SORT_THREADS + threadIdx.x;
       if (e < n) atomicAdd(&h[(keys[e] >> shift) & mask], 1u);
     }
@@ -241,6 +243,12 @@ __device__ __forceinline__ uint32_t block_exclusive_scan_256(uint32_t x, uint32_
 #ifndef GS3D_SCATTER_MINB
 #define GS3D_SCATTER_MINB 4  // blocks per SM the scatter is compiled for (64 registers, 43 KB shared memory each)
 #endif
+#ifndef GS3D_SCATTER_MINB_SMALL
+#define GS3D_SCATTER_MINB_SMALL 6  // same for the 2048-item tiles of the Gaussian-level passes (27 KB each)
+#endif
+#ifndef GS3D_DEPTH_IPT
+#define GS3D_DEPTH_IPT 8  // items per thread of the last depth pass (3 M Gaussians: 1465 tiles instead of 733)
+#endif
 enum { SC_PLAIN = 0, SC_FIRST_DEPTH = 1, SC_LAST_DEPTH = 2, SC_LAST_TILE = 3 };
 constexpr int MAX_TILE_PASSES = 3;  // n_tiles < 2^24
 
@@ -267,11 +275,11 @@ __device__ __forceinline__ uint2 pack_rect(int2 a, int2 b) {
   return make_uint2(((uint32_t)a.x & 0xffffu) | ((uint32_t)a.y << 16), ((uint32_t)w & 0xffffu) | ((uint32_t)h << 16));
 }
 
-template <int MODE, int BITS>
-__global__ void __launch_bounds__(SORT_THREADS, GS3D_SCATTER_MINB)
+template <int MODE, int BITS, int IPT>
+__global__ void __launch_bounds__(SORT_THREADS, (IPT <= 8 ? GS3D_SCATTER_MINB_SMALL : GS3D_SCATTER_MINB))
 scatter_kernel(const ScArgs a) {
-  constexpr int IPT = SORT_IPT;
   constexpr uint32_t NB = 1u << BITS;  // bins
+  constexpr int SORT_TILE = SORT_THREADS * IPT;  // (shadows the namespace constant: this kernel's own tile)
   __shared__ uint32_t s_keys[SORT_TILE];
   __shared__ uint32_t s_vals[SORT_TILE];
   __shared__ uint32_t warp_hist[SORT_WARPS][NB];
@@ -290,7 +298,7 @@ scatter_kernel(const ScArgs a) {
   for (int i = threadIdx.x; i < SORT_WARPS * (int)NB; i += SORT_THREADS) (&warp_hist[0][0])[i] = 0;
   __syncthreads();
 
-  // warp-striped tile: warp w owns items [w*512, (w+1)*512), item (i, lane) = w*512 + i*32 + lane
+  // warp-striped tile: warp w owns items [w*32*IPT, (w+1)*32*IPT), item (i, lane) = w*32*IPT + i*32 + lane
   const size_t warp_base = tile_base + (size_t)warp * (32 * IPT);
   uint32_t k[IPT];
   uint16_t rank[IPT];
@@ -493,7 +501,7 @@ static int radix_pass(const uint32_t *kin, const uint32_t *vin, uint32_t *kout, 
   uint32_t nblocks = div_up(n, (uint32_t)SORT_TILE);
   uint32_t mask = (1u << bits) - 1u;
   GS3D_CUDA(cudaMemsetAsync(rb.totals, 0, RADIX * sizeof(uint32_t), st));
-  radix_hist_kernel<<<nblocks, SORT_THREADS, 0, st>>>(kin, n, shift, mask, nblocks, rb.table, rb.totals, n_dev);
+  radix_hist_kernel<SORT_IPT><<<nblocks, SORT_THREADS, 0, st>>>(kin, n, shift, mask, nblocks, rb.table, rb.totals, n_dev);
   GS3D_LAUNCH_CHECK();
   radix_scan_kernel<<<RADIX, 256, 0, st>>>(nblocks, rb.table, rb.totals);
   GS3D_LAUNCH_CHECK();
@@ -704,36 +712,47 @@ __global__ void copy_u32_kernel(uint32_t n, const uint32_t *__restrict__ a, uint
   if (i < n) b[i] = a[i];
 }
 
-static uint32_t table_elems(uint32_t n) { return RADIX * div_up(n ? n : 1u, (uint32_t)SORT_TILE); }
+static uint32_t table_elems(uint32_t n) { return RADIX * div_up(n ? n : 1u, (uint32_t)(SORT_THREADS * GS3D_DEPTH_IPT)); }
 
 constexpr uint32_t COUNTER_WORDS = 8 * RADIX + 64;    // digit totals [8 passes][RADIX], total / n_eff
 
-template <int MODE>
+template <int MODE, int IPT>
 static int scatter_launch(const ScArgs &a, int bits, cudaStream_t st) {
   if (a.nblocks == 0) return GS3D_OK;
   switch (bits) {
-    case 8: scatter_kernel<MODE, 8><<<a.nblocks, SORT_THREADS, 0, st>>>(a); break;
-    case 7: scatter_kernel<MODE, 7><<<a.nblocks, SORT_THREADS, 0, st>>>(a); break;
-    case 6: scatter_kernel<MODE, 6><<<a.nblocks, SORT_THREADS, 0, st>>>(a); break;
-    case 5: scatter_kernel<MODE, 5><<<a.nblocks, SORT_THREADS, 0, st>>>(a); break;
-    default: scatter_kernel<MODE, 4><<<a.nblocks, SORT_THREADS, 0, st>>>(a); break;
+    case 8: scatter_kernel<MODE, 8, IPT><<<a.nblocks, SORT_THREADS, 0, st>>>(a); break;
+    case 7: scatter_kernel<MODE, 7, IPT><<<a.nblocks, SORT_THREADS, 0, st>>>(a); break;
+    case 6: scatter_kernel<MODE, 6, IPT><<<a.nblocks, SORT_THREADS, 0, st>>>(a); break;
+    case 5: scatter_kernel<MODE, 5, IPT><<<a.nblocks, SORT_THREADS, 0, st>>>(a); break;
+    default: scatter_kernel<MODE, 4, IPT><<<a.nblocks, SORT_THREADS, 0, st>>>(a); break;
   }
+  GS3D_LAUNCH_CHECK();
+  return GS3D_OK;
+}
+template <int MODE>
+static int scatter_launch8(const ScArgs &a, cudaStream_t st) {  // depth passes: always 8 bits
+  if (a.nblocks == 0) return GS3D_OK;
+  scatter_kernel<MODE, 8, GS3D_DEPTH_IPT><<<a.nblocks, SORT_THREADS, 0, st>>>(a);
   GS3D_LAUNCH_CHECK();
   return GS3D_OK;
 }
 
 // histogram + scan + specialised scatter of one pass; `totals` is this pass's own zeroed row
-template <int MODE>
+template <int MODE, bool DEPTH>
 static int radix_pass2(ScArgs a, int bits, uint32_t *table, uint32_t *totals, cudaStream_t st) {
-  a.nblocks = div_up(a.n, (uint32_t)SORT_TILE);
+  // 2048-item tiles only pay off where the scatter is latency-bound on its gather (measured, cfg 2: last depth
+  // pass 64 -> 48 us; the plain depth passes gain nothing and their histogram / scan get longer tables)
+  constexpr int IPT = (DEPTH && MODE == SC_LAST_DEPTH) ? GS3D_DEPTH_IPT : SORT_IPT;
+  a.nblocks = div_up(a.n, (uint32_t)(SORT_THREADS * IPT));
   a.table = table;
   if (a.nblocks == 0) return GS3D_OK;
-  radix_hist_kernel<<<a.nblocks, SORT_THREADS, 0, st>>>(a.keys_in, a.n, a.shift, (1u << bits) - 1u, a.nblocks, table,
-                                                        totals, a.n_dev);
+  radix_hist_kernel<IPT><<<a.nblocks, SORT_THREADS, 0, st>>>(a.keys_in, a.n, a.shift, (1u << bits) - 1u, a.nblocks,
+                                                             table, totals, a.n_dev);
   GS3D_LAUNCH_CHECK();
   radix_scan_kernel<<<RADIX, 256, 0, st>>>(a.nblocks, table, totals);
   GS3D_LAUNCH_CHECK();
-  return scatter_launch<MODE>(a, bits, st);
+  if (IPT != SORT_IPT) return scatter_launch8<MODE>(a, st);
+  return scatter_launch<MODE, SORT_IPT>(a, bits, st);
 }
 
 }  // namespace gs3d
@@ -871,16 +890,16 @@ static int binning_core(uint32_t N, uint32_t n_dub, uint32_t n_tiles_h, uint32_t
     // pass 0: depth -> (kA, vA);  1: -> (kB, vB);  2: -> (kA, vA);  3: -> ids in depth order (vB) + packed rects
     a.keys_in = reinterpret_cast<const uint32_t *>(depth); a.vals_in = nullptr; a.keys_out = kA; a.vals_out = vA;
     a.shift = 0;
-    int rc = radix_pass2<SC_FIRST_DEPTH>(a, 8, table, counters + 0 * RADIX, st);
+    int rc = radix_pass2<SC_FIRST_DEPTH, true>(a, 8, table, counters + 0 * RADIX, st);
     if (rc) return rc;
     a.keys_in = kA; a.vals_in = vA; a.keys_out = kB; a.vals_out = vB; a.shift = 8;
-    rc = radix_pass2<SC_PLAIN>(a, 8, table, counters + 1 * RADIX, st);
+    rc = radix_pass2<SC_PLAIN, true>(a, 8, table, counters + 1 * RADIX, st);
     if (rc) return rc;
     a.keys_in = kB; a.vals_in = vB; a.keys_out = kA; a.vals_out = vA; a.shift = 16;
-    rc = radix_pass2<SC_PLAIN>(a, 8, table, counters + 2 * RADIX, st);
+    rc = radix_pass2<SC_PLAIN, true>(a, 8, table, counters + 2 * RADIX, st);
     if (rc) return rc;
     a.keys_in = kA; a.vals_in = vA; a.keys_out = nullptr; a.vals_out = vB; a.shift = 24;
-    rc = radix_pass2<SC_LAST_DEPTH>(a, 8, table, counters + 3 * RADIX, st);
+    rc = radix_pass2<SC_LAST_DEPTH, true>(a, 8, table, counters + 3 * RADIX, st);
     if (rc) return rc;
   }
   // deterministic offsets: scan of the duplicate counts in depth order (+ start / end = -1)
@@ -915,11 +934,11 @@ static int binning_core(uint32_t N, uint32_t n_dub, uint32_t n_tiles_h, uint32_t
     int rc;
     if (p + 1 < n_pass) {
       a.keys_out = knext;
-      rc = radix_pass2<SC_PLAIN>(a, bits_pp, table, counters + (4 + p) * RADIX, st);
+      rc = radix_pass2<SC_PLAIN, false>(a, bits_pp, table, counters + (4 + p) * RADIX, st);
     } else {
       a.keys_out = sorted_keys ? knext : nullptr;
       a.start = start; a.end = end; a.n_tiles = n_tiles;
-      rc = radix_pass2<SC_LAST_TILE>(a, bits_pp, table, counters + (4 + p) * RADIX, st);
+      rc = radix_pass2<SC_LAST_TILE, false>(a, bits_pp, table, counters + (4 + p) * RADIX, st);
     }
     if (rc) return rc;
     uint32_t *t = kcur; kcur = knext; knext = t;

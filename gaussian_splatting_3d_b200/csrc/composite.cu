@@ -557,9 +557,6 @@ __device__ __forceinline__ void emit_quad(const CompositeParams &p, size_t g, in
 // Early termination: every warp publishes "some pixel still alive" with its arrival; when no warp is alive the
 // producer arms the next stage as a sentinel (0 Gaussians) and the warps leave.
 
-#ifndef GS3D_MBAR_SUSPEND_NS
-#define GS3D_MBAR_SUSPEND_NS 20000u  // upper bound of one hardware suspend; an arrival wakes the warp earlier
-#endif
 constexpr int RS = 4;  // ring stages
 constexpr int RG = 8;  // Gaussians per stage
 
@@ -573,14 +570,24 @@ __device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t byt
   asm volatile("{\n.reg .b64 st;\nmbarrier.arrive.expect_tx.shared::cta.b64 st, [%0], %1;\n}" ::"r"(bar), "r"(bytes)
                : "memory");
 }
-// Blocking wait for the phase with the given parity.  try_wait carries a suspend-time hint, so a warp whose
-// data has not arrived is parked by the hardware instead of re-issuing the probe (without the hint the first
-// ring kernel spent 17 % of all issued instructions in this loop: profiles/r2_ncu_bwd_ring_v1.txt).
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+// Blocking wait for the phase with the given parity.  One try_wait (the common case: the data is already there),
+// then a timed sleep between probes.  ncu history (profiles/): a bare try_wait loop spent 17 % of all issued
+// instructions probing; try_wait with a suspend-time hint compiles to TRYWAIT + NANOSLEEP.SYNCS, which wakes on
+// every mbarrier event of the SM -- 289 probes per blocked wait, 23 % of the kernel's instructions
+// (profiles/r2_ncu_bwd_ring_v2.txt).  A warp that has to wait is waiting for a slower warp of its tile, i.e. for
+// microseconds: a plain nanosleep of GS3D_WAIT_NS between probes costs it nothing and frees the issue slots.
+#ifndef GS3D_WAIT_NS
+#define GS3D_WAIT_NS 200u
+#endif
+__device__ __forceinline__ bool mbar_try(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
   asm volatile(
-      "{\n.reg .pred P1;\nLAB_WAIT:\nmbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1, %2;\n@P1 bra DONE;\n"
-      "bra LAB_WAIT;\nDONE:\n}" ::"r"(bar), "r"(parity), "r"(GS3D_MBAR_SUSPEND_NS)
-      : "memory");
+      "{\n.reg .pred P1;\nmbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2;\nselp.u32 %0, 1, 0, P1;\n}"
+      : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, uint32_t sleep_ns = GS3D_WAIT_NS) {
+  while (!mbar_try(bar, parity)) __nanosleep(sleep_ns);
 }
 // 1-D bulk copy global -> shared (TMA engine, UBLKCP); bytes is a multiple of 16, both addresses 16-byte aligned
 __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar) {

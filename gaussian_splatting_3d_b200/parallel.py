@@ -144,6 +144,7 @@ class FlatGradients:
             self.multicast_ptr = mc if mc else None
         self.module = None
         self._dirty = False
+        self._backwards_since_zero = 0
         # side stream for the per-step resets and the mark broadcast: they overlap the forward kernels and
         # the projection backward instead of sitting on the critical path between two barriers
         self._aux = torch.cuda.Stream(device=dev) if (self.push and dev.type == "cuda") else None
@@ -205,6 +206,7 @@ class FlatGradients:
 
     def zero(self):
         self._check_attached()
+        self._backwards_since_zero = 0
         if self.push and self.module is not None:
             from . import ops
 
@@ -245,6 +247,15 @@ class FlatGradients:
         if self.module is None:
             loss.backward()  # plain autograd accumulation into the aliased .grad views
         else:
+            if self.g2d is not None and self._backwards_since_zero > 0:
+                # a second view in the same step: the persistent 2-D gradient scratch still holds the previous
+                # view's d loss / d (mean2d, cov2d, alpha) -- they belong to THAT view's projection and were consumed
+                # by its projection backward.  Clear the marked rows (the marks themselves stay: they describe
+                # the step's union of touched leaf rows).
+                from . import ops
+
+                ops.rows_zero_marked(self.touched, self.g2d, clear_marks=False)
+            self._backwards_since_zero += 1
             # the attached renderer's forward made a fresh one-element leaf its only differentiable input
             # (gs/renderer.py splat_sh): backward() writes the leaf gradients into this object's buffers itself
             anchor = (self.module._state or {}).get("anchor") if hasattr(self.module, "_state") else None

@@ -285,3 +285,33 @@ def test_gpu_flat_gradients_sparse_reset_matches_plain_autograd():
             assert float(ga.reshape(ga.shape[0], -1)[zero_b].abs().max()) == 0.0, k      # no stale rows
             # atomics order differs between the two runs: 1e-3 relative (gradient tolerance of the north star)
             assert float((ga - gb).abs().max()) <= 1e-3 * float(gb.abs().max()) + 1e-12, k
+
+
+@pytest.mark.gpu
+def test_gpu_flat_gradients_several_views_per_step():
+    """Several views between two zero() calls (view-batched training on one GPU, cfg 4): the flat buffer must
+    hold the SUM of the views' gradients.  The persistent 2-D gradient scratch (d loss / d mean2d, cov2d, alpha) is
+    per view: a stale row would push the previous view's 2-D gradient through this view's projection."""
+    from gaussian_splatting_3d_b200 import parallel as P
+    from gaussian_splatting_3d_b200 import synthetic as S
+
+    cam = S.make_camera("cfg1")
+    sc = S.make_scene("cfg1", seed=11)
+    views = [sc["c2w"]] + S.ring_cameras(4, radius=7.0)[:2]
+    tgts = [S.make_target(cam, 20 + i).to(DEV) for i in range(len(views))]
+    a = S.renderer_from_scene(sc, S.make_cfg(device=DEV, sh_order=sc["C"]))
+    b = S.renderer_from_scene(sc, S.make_cfg(device=DEV, sh_order=sc["C"]))
+    a.train()
+    b.train()
+    flat = P.FlatGradients(a, sparse_reset=True).attach(a)
+    for step in range(2):  # twice: the reset between steps must cope with the union of the views' marks
+        flat.zero()
+        for p in b.parameters():
+            p.grad = None
+        for v, t in zip(views, tgts):
+            c2w = v.to(DEV)
+            flat.backward_into(((a(c2w, cam) - t) ** 2).mean())
+            ((b(c2w, cam) - t) ** 2).mean().backward()  # plain autograd accumulation
+        for k in NAMES:
+            ga, gb = getattr(a, k).grad, getattr(b, k).grad
+            assert float((ga - gb).abs().max()) <= 1e-3 * float(gb.abs().max()) + 1e-12, (step, k)
