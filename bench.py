@@ -51,6 +51,12 @@ def parse():
                          "NVLink/NVSwitch + small all-reduce; 'sparse' = all-reduce of the union of touched "
                          "rows only; 'allreduce' = one dense NCCL all-reduce; 'push' (= 'auto') = each rank "
                          "adds the rows it touched into every rank's result buffer over NVSwitch multicast")
+    ap.add_argument("--yaw-step", type=float, default=0.5,
+                    help="N>1 (weak scaling, one view per rank): yaw between neighbouring ranks' poses in degrees.  "
+                         "The cfg-2 scene covers the image with a 5 %% margin (about +-3.8 degrees of yaw): inside "
+                         "it every rank's view is the cfg-2 workload; further out (e.g. the 2-degree steps of round "
+                         "1 at 8 ranks: +-7 degrees) the scene's lateral boundary enters the frame, its tiles never "
+                         "saturate and those views cost up to 13 %% more on ONE GPU (tools/view_costs.py)")
     return ap.parse_args()
 
 
@@ -111,13 +117,14 @@ def phys_gpu_index(local_rank):
 
 # ---------------------------------------------------------------- shared helpers
 
-def views_for(world, torch):
-    """Identity pose for rank 0's cfg-2 view; other ranks yaw by 2 degrees steps around it."""
+def views_for(world, torch, yaw_step=0.5):
+    """One pose per rank: the cfg-2 identity pose yawed by `yaw_step` degrees between neighbouring ranks,
+    centred on the identity (world == 1: the identity itself)."""
     import math
 
     out = []
     for i in range(world):
-        a = math.radians(2.0 * (i - (world - 1) / 2.0)) if world > 1 else 0.0
+        a = math.radians(yaw_step * (i - (world - 1) / 2.0)) if world > 1 else 0.0
         c2w = torch.tensor([[math.cos(a), 0.0, math.sin(a), 0.0],
                             [0.0, 1.0, 0.0, 0.0],
                             [-math.sin(a), 0.0, math.cos(a), 0.0]], dtype=torch.float32)
@@ -268,7 +275,7 @@ def run_ours(args, rank, local_rank, world):
         tgt_hosts = [S.make_target(cam, i).pin_memory() for i in my_views]
         n_views_step = 8
     else:
-        c2w_hosts = [views_for(world, torch)[rank].pin_memory()]
+        c2w_hosts = [views_for(world, torch, args.yaw_step)[rank].pin_memory()]
         tgt_hosts = [S.make_target(cam, rank).pin_memory()]
         n_views_step = world
     c2w_devs = [c.to(dev) for c in c2w_hosts]
@@ -483,7 +490,9 @@ def run_ours(args, rank, local_rank, world):
         "higher_is_better": True, "scaling": "strong" if cfg4 else "weak", "vs_baseline": None, "dtype": "f32",
         "data": "synthetic",
         "config": {"workload": workload_desc(name, N, C, cam, n_views_step), "n_dub": n_dub,
-                   "views_per_step": n_views_step, "parallelism": f"dp{world}" if world > 1 else "single"},
+                   "views_per_step": n_views_step, "parallelism": f"dp{world}" if world > 1 else "single",
+                   **({"rank_poses": f"cfg-2 pose yawed by {args.yaw_step} degrees between neighbouring ranks"}
+                      if (world > 1 and not cfg4) else {})},
         "impl_details": {"views_per_rank": n_views_rank, "dp_exchange": dp_exchange_desc(flat, world, N),
                          "gradient_buffers": "one persistent flat buffer aliased by .grad; per-step reset clears "
                                              "only the rows the previous backward marked",
@@ -650,8 +659,10 @@ def stage_rooflines(kernels_ms, N, C, cam, n_dub, views, staged, pairs, ncu_ok, 
     algo = {
         # read mean 12 + qvec 16 + svec 12 + alpha 4; write the 48-byte record + rect 16 + depth 4 + mask 1
         "K1_project_cull": views * N * 89,  # (the kernel's own necessary traffic is 44 + 48 record + 21 = 113 B)
-        # own algorithm (DESIGN 'K2'): N-level depth passes + emit + tile passes + ranges
-        "K2_binning": views * N * (4 + 4 * 24 + 8) + n_dub * views * (8 + 2 * 24 + 4),
+        # own algorithm (DESIGN 'K2'): per Gaussian 4 depth passes (histogram 4 B + scatter: 4 -> 8, 8 -> 8, 8 -> 8,
+        # 8 + 16 rect gather -> 4 + 8) + count 8 + emit 12 = 116 B; per duplicate emit 8 + pass 0 (4 + 8 + 8) + last
+        # pass (4 + 8 + 4, keys dropped, ranges extracted in the same kernel) = 44 B
+        "K2_binning": views * N * 116 + n_dub * views * 44,
         "K3_composite_fwd": staged_fwd * per_dup + views * px * 12,
         "K4a_composite_bwd": staged_bwd * (per_dup + 4 * (7 + 3 * CC)) + views * px * 36,
         # every row: mask + the three upstream gradients (29 B); rows with a gradient (the marked ones) also read the
@@ -672,6 +683,14 @@ def stage_rooflines(kernels_ms, N, C, cam, n_dub, views, staged, pairs, ncu_ok, 
         except Exception:
             ncu = {}
     out = {}
+    meta = ncu.get("_meta") or {}
+    if meta.get("lib_sha256_16"):  # was the committed ncu capture taken from the library that is loaded now?
+        import hashlib
+
+        lib = ROOT / "gaussian_splatting_3d_b200" / "libgs3d_b200.so"
+        now = hashlib.sha256(lib.read_bytes()).hexdigest()[:16] if lib.exists() else None
+        out["_ncu_capture"] = {"lib_sha256_16": meta["lib_sha256_16"], "loaded_lib_sha256_16": now,
+                               "same_build": now == meta["lib_sha256_16"], "capture": meta.get("capture")}
     for k, ms in kernels_ms.items():
         if k not in algo or ms <= 0:
             continue
@@ -699,7 +718,7 @@ def stage_rooflines(kernels_ms, N, C, cam, n_dub, views, staged, pairs, ncu_ok, 
         if util:
             o["ncu_utilisation_pct_of_peak"] = util
         out[k] = o
-    kk = {k: v for k, v in kernels_ms.items() if k in out}
+    kk = {k: v for k, v in kernels_ms.items() if k in out and not k.startswith("_")}
     dom = max(kk, key=kk.get) if kk else None
     return out, dom
 

@@ -359,18 +359,27 @@ marks_broadcast_kernel(const MarkArgs a) {
 struct ZeroArgs {
   uint8_t *marks;
   uint32_t N;
-  int n_seg, clear;
+  int n_seg, clear, n_units;
   float *base[MAX_SEG];
   uint32_t width[MAX_SEG];
+  uint32_t unit0[MAX_SEG];  // first store unit of the block: a unit is one float4 (vec) or one float
+  int vec[MAX_SEG];
 };
 
 // zero the rows of every marked Gaussian in all blocks, then (clear != 0) the marks themselves
 __global__ void __launch_bounds__(256)
 rows_zero_marked_kernel(const ZeroArgs a) {
+  // one store unit per lane: a row of all blocks (cfg 2: 48 + 3 + 4 + 3 + 1 floats, + 2 + 4 + 1 of the 2-D gradient
+  // scratch) is 24 units -- one store instruction per marked row instead of one per block and 32 floats
   const int lane = threadIdx.x & 31;
   for_each_marked(a.marks, a.N, a.clear, [&](size_t g) {
-    for (int s = 0; s < a.n_seg; ++s)
-      for (uint32_t k = lane; k < a.width[s]; k += 32) a.base[s][g * a.width[s] + k] = 0.0f;
+    for (int u = lane; u < a.n_units; u += 32) {
+      int s = 0;
+      while (s + 1 < a.n_seg && (uint32_t)u >= a.unit0[s + 1]) ++s;
+      const uint32_t k = u - a.unit0[s];
+      if (a.vec[s]) *reinterpret_cast<float4 *>(a.base[s] + g * a.width[s] + 4 * k) = make_float4(0.f, 0.f, 0.f, 0.f);
+      else a.base[s][g * a.width[s] + k] = 0.0f;
+    }
   });
 }
 
@@ -489,6 +498,9 @@ int gs3d_rows_zero_marked(uint8_t *marks, uint32_t N, int n_blocks, const uint64
     a.base[s] = reinterpret_cast<float *>(static_cast<uintptr_t>(block_ptrs_host[s]));
     a.width[s] = block_widths_host[s];
     GS3D_REQUIRE(a.base[s] && a.width[s] > 0, GS3D_EINVAL, "rows_zero: bad block %d", s);
+    a.vec[s] = (a.width[s] % 4 == 0 && (block_ptrs_host[s] & 15) == 0) ? 1 : 0;
+    a.unit0[s] = (uint32_t)a.n_units;
+    a.n_units += (int)(a.vec[s] ? a.width[s] / 4 : a.width[s]);
   }
   rows_zero_marked_kernel<<<div_up(N, 4096u), 256, 0, as_stream(stream)>>>(a);  // 512 marks per warp
   GS3D_LAUNCH_CHECK();

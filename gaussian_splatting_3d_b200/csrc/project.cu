@@ -511,22 +511,20 @@ __device__ __forceinline__ void project_backward_one(const float *p, const float
   g.gq[3] = o.qinv * (gqn[3] - z * dotv);
 }
 
-__global__ void __launch_bounds__(256)
-project_backward_kernel(uint32_t N, const uint8_t *__restrict__ mask,
-                        const float *__restrict__ mean, const float *__restrict__ qvec,
-                        const float *__restrict__ svec_param, const float *__restrict__ alpha_param,
-                        int svec_act, int alpha_act, const float *__restrict__ c2w_g, int detach,
-                        const float *__restrict__ gm2d, const float *__restrict__ gcov,
-                        const float *__restrict__ gdepth, const float *__restrict__ galpha,
-                        float *__restrict__ gmean, float *__restrict__ gqvec,
-                        float *__restrict__ gsvec, float *__restrict__ galpha_param,
-                        float *__restrict__ adc_acc, int adc_mode, int accumulate) {
-  __shared__ float c2w[12];
-  if (threadIdx.x < 12) c2w[threadIdx.x] = c2w_g[threadIdx.x];
-  __syncthreads();
-  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= N) return;
-  bool keep = mask ? mask[i] != 0 : true;
+struct K4bArgs {
+  uint32_t N;
+  const uint8_t *mask;
+  const float *mean, *qvec, *svec_param, *alpha_param;
+  int svec_act, alpha_act;
+  const float *c2w_g;
+  int detach;
+  const float *gm2d, *gcov, *gdepth, *galpha;
+  float *gmean, *gqvec, *gsvec, *galpha_param, *adc_acc;
+  int adc_mode, accumulate;
+};
+
+// One Gaussian of the projection backward.  keep == false: no gradient reaches this row (culled / unmarked).
+__device__ __forceinline__ void k4b_row(const K4bArgs &a, const float *c2w, uint32_t i, bool keep) {
   LeafGrad g;
   float ga = 0.0f;
   float2 gm = make_float2(0.f, 0.f);
@@ -535,45 +533,46 @@ project_backward_kernel(uint32_t N, const uint8_t *__restrict__ mask,
     // A view touches a small fraction of the Gaussians (cfg 2: ~2 %): when every upstream gradient of
     // this Gaussian is zero the chain rule gives zeros -- skip the parameter loads and the arithmetic
     // (and, when accumulating, the read-modify-write).  NaN/Inf upstream values compare unequal to 0.
-    gm = reinterpret_cast<const float2 *>(gm2d)[i];
-    gc = reinterpret_cast<const float4 *>(gcov)[i];
-    const float ga_up = galpha ? galpha[i] : 0.0f;
-    const float gd_up = gdepth ? gdepth[i] : 0.0f;
+    gm = reinterpret_cast<const float2 *>(a.gm2d)[i];
+    gc = reinterpret_cast<const float4 *>(a.gcov)[i];
+    const float ga_up = a.galpha ? a.galpha[i] : 0.0f;
+    const float gd_up = a.gdepth ? a.gdepth[i] : 0.0f;
     if (gm.x == 0.f && gm.y == 0.f && gc.x == 0.f && gc.y == 0.f && gc.z == 0.f && gc.w == 0.f &&
         ga_up == 0.f && gd_up == 0.f)
       keep = false;
   }
   if (keep) {
-    float p[3] = {mean[3 * (size_t)i], mean[3 * (size_t)i + 1], mean[3 * (size_t)i + 2]};
-    float4 q4 = reinterpret_cast<const float4 *>(qvec)[i];
+    float p[3] = {a.mean[3 * (size_t)i], a.mean[3 * (size_t)i + 1], a.mean[3 * (size_t)i + 2]};
+    float4 q4 = reinterpret_cast<const float4 *>(a.qvec)[i];
     float q[4] = {q4.x, q4.y, q4.z, q4.w};
-    float s[3] = {act_exp(svec_param[3 * (size_t)i], svec_act),
-                  act_exp(svec_param[3 * (size_t)i + 1], svec_act),
-                  act_exp(svec_param[3 * (size_t)i + 2], svec_act)};
+    float s[3] = {act_exp(a.svec_param[3 * (size_t)i], a.svec_act),
+                  act_exp(a.svec_param[3 * (size_t)i + 1], a.svec_act),
+                  act_exp(a.svec_param[3 * (size_t)i + 2], a.svec_act)};
     float gm2[2] = {gm.x, gm.y};
     float gS[4] = {gc.x, gc.y, gc.z, gc.w};
-    project_backward_one(p, q, s, c2w, gm2, gS, gdepth ? gdepth[i] : 0.0f, detach, g);
-    if (svec_act) {
+    project_backward_one(p, q, s, c2w, gm2, gS, a.gdepth ? a.gdepth[i] : 0.0f, a.detach, g);
+    if (a.svec_act) {
       g.gs[0] *= s[0]; g.gs[1] *= s[1]; g.gs[2] *= s[2];
     }
-    if (galpha) {
-      ga = galpha[i];
-      if (alpha_act) {
-        float a = act_sigmoid(alpha_param[i], 1);
-        ga *= a * (1.0f - a);
+    if (a.galpha) {
+      ga = a.galpha[i];
+      if (a.alpha_act) {
+        float al = act_sigmoid(a.alpha_param[i], 1);
+        ga *= al * (1.0f - al);
       }
     }
-    if (adc_mode && adc_acc) {  // sh_renderer.py:612-623, split_type "2d_mean_grad"
+    if (a.adc_mode && a.adc_acc) {  // sh_renderer.py:612-623, split_type "2d_mean_grad"
       float nrm = sqrtf(gm.x * gm.x + gm.y * gm.y);
-      if (adc_mode == 1) adc_acc[i] = fmaxf(adc_acc[i], nrm);
-      else adc_acc[i] += nrm;
+      if (a.adc_mode == 1) a.adc_acc[i] = fmaxf(a.adc_acc[i], nrm);
+      else a.adc_acc[i] += nrm;
     }
   } else {
     g.gp[0] = g.gp[1] = g.gp[2] = 0.f;
     g.gq[0] = g.gq[1] = g.gq[2] = g.gq[3] = 0.f;
     g.gs[0] = g.gs[1] = g.gs[2] = 0.f;
   }
-  if (accumulate) {  // several views per step: sum into the caller's gradient buffers
+  float *gmean = a.gmean, *gqvec = a.gqvec, *gsvec = a.gsvec, *galpha_param = a.galpha_param;
+  if (a.accumulate) {  // several views per step: sum into the caller's gradient buffers
     if (!keep) return;
     gmean[3 * (size_t)i] += g.gp[0]; gmean[3 * (size_t)i + 1] += g.gp[1]; gmean[3 * (size_t)i + 2] += g.gp[2];
     float4 q0 = reinterpret_cast<float4 *>(gqvec)[i];
@@ -586,6 +585,61 @@ project_backward_kernel(uint32_t N, const uint8_t *__restrict__ mask,
   reinterpret_cast<float4 *>(gqvec)[i] = make_float4(g.gq[0], g.gq[1], g.gq[2], g.gq[3]);
   gsvec[3 * (size_t)i] = g.gs[0]; gsvec[3 * (size_t)i + 1] = g.gs[1]; gsvec[3 * (size_t)i + 2] = g.gs[2];
   if (galpha_param) galpha_param[i] = ga;
+}
+
+__global__ void __launch_bounds__(256)
+project_backward_kernel(const K4bArgs a) {
+  __shared__ float c2w[12];
+  if (threadIdx.x < 12) c2w[threadIdx.x] = a.c2w_g[threadIdx.x];
+  __syncthreads();
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= a.N) return;
+  k4b_row(a, c2w, i, a.mask ? a.mask[i] != 0 : true);
+}
+
+// Sparse row filter (accumulate == 2: the mask is the compositing backward's `touched` marks, ~2 % of the rows):
+// with one thread per Gaussian almost every warp would run the whole chain rule for a single live lane -- 67 k
+// rows cost 57 us at cfg 2, latency-bound.  Here a warp reads 512 marks (16 bytes per lane), compacts the marked
+// indices into shared memory and processes them 32 at a time with all lanes busy.  Accumulating only.
+__global__ void __launch_bounds__(256)
+project_backward_marked_kernel(const K4bArgs a) {
+  __shared__ float c2w[12];
+  __shared__ uint32_t s_idx[8][512];
+  if (threadIdx.x < 12) c2w[threadIdx.x] = a.c2w_g[threadIdx.x];
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const size_t w0 = ((size_t)blockIdx.x * 8 + warp) * 512;  // first Gaussian of this warp
+  if (w0 >= a.N) return;
+  const size_t c0 = w0 + (size_t)lane * 16;
+  uint32_t bits = 0;  // one bit per marked Gaussian of this lane's 16
+  if (c0 + 16 <= a.N && (reinterpret_cast<uintptr_t>(a.mask) & 15) == 0) {
+    const uint4 v = *reinterpret_cast<const uint4 *>(a.mask + c0);
+    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+    for (int q = 0; q < 4; ++q)
+#pragma unroll
+      for (int b = 0; b < 4; ++b)
+        if ((w[q] >> (8 * b)) & 0xffu) bits |= 1u << (4 * q + b);
+  } else {
+    for (int b = 0; b < 16; ++b)
+      if (c0 + b < a.N && a.mask[c0 + b]) bits |= 1u << b;
+  }
+  const uint32_t cnt = __popc(bits);
+  uint32_t incl = cnt;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const uint32_t y = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl += y;
+  }
+  const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
+  uint32_t pos = incl - cnt;
+  while (bits) {
+    const int b = __ffs(bits) - 1;
+    bits &= bits - 1;
+    s_idx[warp][pos++] = (uint32_t)(c0 + b);
+  }
+  __syncwarp();
+  for (uint32_t j = lane; j < total; j += 32) k4b_row(a, c2w, s_idx[warp][j], true);
 }
 
 static int read_count(unsigned long long *dev_total, int64_t *n_dub_host, cudaStream_t st) {
@@ -649,9 +703,11 @@ int gs3d_project_gaussians_backward(uint32_t N, const float *mean, const float *
   GS3D_REQUIRE(mean && qvec && svec && c2w && grad_mean2d && grad_cov2d && grad_mean && grad_qvec &&
                    grad_svec,
                GS3D_EINVAL, "gs3d_project_gaussians_backward: null argument");
-  project_backward_kernel<<<div_up(N, 256u), 256, 0, as_stream(stream)>>>(
-      N, nullptr, mean, qvec, svec, nullptr, 0, 0, c2w, detach_depth, grad_mean2d, grad_cov2d,
-      grad_depth, nullptr, grad_mean, grad_qvec, grad_svec, nullptr, nullptr, 0, 0);
+  K4bArgs a = {};
+  a.N = N; a.mean = mean; a.qvec = qvec; a.svec_param = svec; a.c2w_g = c2w; a.detach = detach_depth;
+  a.gm2d = grad_mean2d; a.gcov = grad_cov2d; a.gdepth = grad_depth;
+  a.gmean = grad_mean; a.gqvec = grad_qvec; a.gsvec = grad_svec;
+  project_backward_kernel<<<div_up(N, 256u), 256, 0, as_stream(stream)>>>(a);
   GS3D_LAUNCH_CHECK();
   return GS3D_OK;
 }
@@ -735,10 +791,16 @@ int gs3d_project_backward_fused(uint32_t N, const uint8_t *mask, const float *me
   GS3D_REQUIRE(mean && qvec && svec_param && alpha_param && c2w && grad_mean2d && grad_cov2d &&
                    grad_alpha && grad_mean && grad_qvec && grad_svec_param && grad_alpha_param,
                GS3D_EINVAL, "gs3d_project_backward_fused: null argument");
-  project_backward_kernel<<<div_up(N, 256u), 256, 0, as_stream(stream)>>>(
-      N, mask, mean, qvec, svec_param, alpha_param, svec_act, alpha_act, c2w, detach_depth,
-      grad_mean2d, grad_cov2d, nullptr, grad_alpha, grad_mean, grad_qvec, grad_svec_param,
-      grad_alpha_param, grad_mean_acc, adc_mode, accumulate);
+  K4bArgs a = {};
+  a.N = N; a.mask = mask; a.mean = mean; a.qvec = qvec; a.svec_param = svec_param; a.alpha_param = alpha_param;
+  a.svec_act = svec_act; a.alpha_act = alpha_act; a.c2w_g = c2w; a.detach = detach_depth;
+  a.gm2d = grad_mean2d; a.gcov = grad_cov2d; a.gdepth = nullptr; a.galpha = grad_alpha;
+  a.gmean = grad_mean; a.gqvec = grad_qvec; a.gsvec = grad_svec_param; a.galpha_param = grad_alpha_param;
+  a.adc_acc = grad_mean_acc; a.adc_mode = adc_mode; a.accumulate = accumulate ? 1 : 0;
+  if (accumulate == 2 && mask)  // sparse row filter: compact the marked rows first
+    project_backward_marked_kernel<<<div_up(N, 4096u), 256, 0, as_stream(stream)>>>(a);
+  else
+    project_backward_kernel<<<div_up(N, 256u), 256, 0, as_stream(stream)>>>(a);
   GS3D_LAUNCH_CHECK();
   return GS3D_OK;
 }

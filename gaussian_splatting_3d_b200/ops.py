@@ -306,9 +306,11 @@ def composite_sh_backward(records, sh, start, end, gaussian_ids, out, grad_out, 
 # ---------------------------------------------------------------- a9 + a10
 def project_backward_fused(mask, mean, qvec, svec_param, alpha_param, svec_act, alpha_act, c2w,
                            detach_depth, g_mean2d, g_cov, g_alpha, grad_mean_acc=None, adc_mode=0,
-                           out=None, accumulate=False):
+                           out=None, accumulate=False, sparse_filter=False):
     """`out` = (grad_mean, grad_qvec, grad_svec_param, grad_alpha_param) caller buffers (e.g. views of
-    one flat all-reduce buffer); with accumulate=True the kernel adds into them."""
+    one flat all-reduce buffer); with accumulate=True the kernel adds into them.  sparse_filter=True (with
+    accumulate): `mask` marks only a few percent of the rows (the compositing backward's `touched` marks) --
+    the kernel compacts them first."""
     N = mean.size(0)
     dev = mean.device
     if out is None:
@@ -331,7 +333,8 @@ def project_backward_fused(mask, mean, qvec, svec_param, alpha_param, svec_act, 
     check(capi.lib.gs3d_project_backward_fused(
         N, ptr(mask), ptr(mean), ptr(qvec), ptr(svec_param), ptr(alpha_param), int(svec_act),
         int(alpha_act), ptr(c2w), 1 if detach_depth else 0, ptr(g_mean2d), ptr(g_cov), ptr(g_alpha),
-        ptr(gm), ptr(gq), ptr(gs), ptr(ga), ptr(grad_mean_acc), int(adc_mode), 1 if accumulate else 0,
+        ptr(gm), ptr(gq), ptr(gs), ptr(ga), ptr(grad_mean_acc), int(adc_mode),
+        (2 if sparse_filter else 1) if accumulate else 0,
         _stream(mean)), "project_backward_fused")
     return gm, gq, gs, ga
 

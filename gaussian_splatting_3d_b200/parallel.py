@@ -438,7 +438,8 @@ def clip_rects_to_band(aabb_topleft, aabb_bottomright, row_begin, row_end):
 @torch.no_grad()
 def render_band(renderer, c2w, camera_info, row_begin=None, row_end=None, k1=None):
     """Forward-render tile rows [row_begin, row_end) of one frame (None = all rows).  Returns the
-    full-size [H,W,3] buffer in which only the band's rows are written, plus the K1 outputs."""
+    full-size [H,W,3] buffer in which only the band's rows are DEFINED (the rest is uninitialised memory), plus
+    the K1 outputs."""
     from . import ops
 
     dev = renderer.mean.device
@@ -464,8 +465,12 @@ def render_band(renderer, c2w, camera_info, row_begin=None, row_end=None, k1=Non
     ops.tile_culling_aabb_start_end(tl, br, ids, start, end, depth_b, nth, ntw, check_count=False)
     if n_band:
         ids = torch.index_select(index, 0, ids)
-    out = torch.zeros(H * W * 3, dtype=torch.float32, device=dev)
-    topleft = torch.tensor([-cam.cx / cam.fx, -cam.cy / cam.fy], dtype=torch.float32).to(dev)
+    # only the band's rows are ever read back: empty tiles of the band keep the zero fill, the rest of the
+    # full-size buffer stays uninitialised (a 4K frame is 99.5 MB: no full fill per band)
+    out = torch.empty(H * W * 3, dtype=torch.float32, device=dev)
+    out[row_begin * tile * W * 3: min(row_end * tile, H) * W * 3].zero_()
+    topleft = renderer._topleft(cam) if hasattr(renderer, "_topleft") else \
+        torch.tensor([-cam.cx / cam.fx, -cam.cy / cam.fy], dtype=torch.float32).to(dev)
     bg = renderer.bg_rgb if renderer.bg else None
     ops.composite_sh_forward(k1["records"], renderer.sh_coeffs.data, start, end, ids, out, topleft, c2w, tile,
                              nth, ntw, 1.0 / cam.fx, 1.0 / cam.fy, H, W, C, renderer.T_thresh, bg_rgb=bg,
@@ -489,7 +494,8 @@ def tile_sharded_render(renderer, c2w, camera_info, group=None, gather=True):
         renderer.mean.data, renderer.qvec.data, renderer.svec_before_activation.data,
         renderer.alpha_before_activation.data, renderer._svec_code, renderer._alpha_code,
         c2w.contiguous().float(), cam, renderer.frustum_culling_radius, renderer.skip_frustum_culling,
-        renderer.tile_culling_radius, tile, cnt=None, want_records=True, want_activated=False)
+        renderer.tile_culling_radius, tile, cnt=None, want_records=True, want_activated=False,
+        sync_count=False, want_projection=False)  # (the whole-frame duplicate count is not needed here)
     bands = balanced_bands(row_duplicate_counts(k1["tl"], k1["br"], nth), world)
     r0, r1 = bands[rank]
     img, _ = render_band(renderer, c2w, cam, r0, r1, k1=k1)

@@ -274,7 +274,10 @@ int gs3d_composite_rgb_backward(uint32_t M, const float *records, const float *c
  * grad_mean_acc[i] = max(., ||grad_mean2d_i||) (adc_mode 1, split_reduction "max") or
  * += ||grad_mean2d_i|| (adc_mode 2, "mean") for split_type "2d_mean_grad".
  * Leaf gradients are OVERWRITTEN, or -- accumulate != 0, used when several views share one
- * gradient buffer (view-sharded training) -- ADDED for the Gaussians with mask != 0. */
+ * gradient buffer (view-sharded training) -- ADDED for the Gaussians with mask != 0.
+ * accumulate == 2: same as 1, and `mask` is a SPARSE row filter (the `touched` marks of
+ * gs3d_composite_sh_backward_peers: a few percent of the rows): the marked rows are compacted per warp first so
+ * that all lanes work (one thread per Gaussian would run the chain rule with one live lane per warp). */
 int gs3d_project_backward_fused(uint32_t N, const uint8_t *mask, const float *mean,
                                 const float *qvec, const float *svec_param,
                                 const float *alpha_param, int svec_act, int alpha_act,

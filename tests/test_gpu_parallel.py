@@ -38,9 +38,7 @@ def test_bands_compose_to_full_frame_single_gpu():
         for a, b in bands:
             img, _ = P.render_band(r, c2w, cam, a, b, k1=k1)
             y0, y1 = a * 16, min(b * 16, cam.h)
-            acc[y0:y1] = img[y0:y1]
-            outside = torch.cat([img[:y0], img[y1:]])
-            assert float(outside.abs().max()) == 0.0 if outside.numel() else True
+            acc[y0:y1] = img[y0:y1]  # (rows outside the band are undefined: the buffer is not filled)
         assert torch.equal(acc, full)
         loads = [int(rc[a:b].sum()) for a, b in bands]
         assert max(loads) <= sum(loads) / world + int(rc.max())
