@@ -61,44 +61,42 @@ radix_hist_kernel(const uint32_t *__restrict__ keys, uint32_t n, int shift, uint
   if (c) atomicAdd(&totals[threadIdx.x], c);
 }
 
-// One block per digit: base = sum of totals of lower digits, then exclusive scan along the blocks.
+// One block per digit: base = sum of totals of lower digits, then exclusive scan along the blocks.  Every thread
+// owns a run of consecutive blocks (two sequential sweeps around ONE block-wide scan: the table rows are a few
+// thousand entries, a chunked scan with four barriers per 256 entries took 7-13 us per pass).
 __global__ void __launch_bounds__(256)
 radix_scan_kernel(uint32_t nblocks, uint32_t *__restrict__ table, const uint32_t *__restrict__ totals) {
   __shared__ uint32_t red[8];
-  __shared__ uint32_t carry_s;
+  __shared__ uint32_t wsum[8];
   const int d = blockIdx.x;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   uint32_t v = (threadIdx.x < d) ? totals[threadIdx.x] : 0u;
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
   if (lane == 0) red[warp] = v;
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    uint32_t s = 0;
-    for (int w = 0; w < 8; ++w) s += red[w];
-    carry_s = s;
-  }
-  __syncthreads();
   uint32_t *row = table + (size_t)d * nblocks;
-  for (uint32_t b0 = 0; b0 < nblocks; b0 += 256) {
-    uint32_t b = b0 + threadIdx.x;
-    uint32_t x = (b < nblocks) ? row[b] : 0u;
-    uint32_t incl = x;
+  const uint32_t per = (nblocks + 255u) / 256u;
+  const uint32_t b0 = min(nblocks, threadIdx.x * per), b1 = min(nblocks, b0 + per);
+  uint32_t s = 0;
+  for (uint32_t b = b0; b < b1; ++b) s += row[b];
+  uint32_t incl = s;
 #pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-      uint32_t y = __shfl_up_sync(0xffffffffu, incl, o);
-      if (lane >= o) incl += y;
-    }
-    __syncthreads();  // red[] reuse + carry_s read ordering
-    if (lane == 31) red[warp] = incl;
-    __syncthreads();
-    uint32_t wbase = 0;
-    for (int w = 0; w < warp; ++w) wbase += red[w];
-    uint32_t carry = carry_s;
-    if (b < nblocks) row[b] = carry + wbase + incl - x;
-    __syncthreads();
-    if (threadIdx.x == 255) carry_s = carry + wbase + incl;
-    __syncthreads();
+  for (int o = 1; o < 32; o <<= 1) {
+    uint32_t y = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl += y;
+  }
+  if (lane == 31) wsum[warp] = incl;
+  __syncthreads();
+  uint32_t run = incl - s;
+#pragma unroll
+  for (int w = 0; w < 8; ++w) {
+    run += red[w];                 // digits below this one
+    if (w < warp) run += wsum[w];  // blocks of the warps before this one
+  }
+  for (uint32_t b = b0; b < b1; ++b) {
+    const uint32_t x = row[b];
+    row[b] = run;
+    run += x;
   }
 }
 
@@ -411,20 +409,24 @@ scatter_kernel(const ScArgs a) {
   }
 }
 
-// duplicate counts in depth order from the packed rects (streaming) -> per-block sums
+// duplicate counts in depth order from the packed rects (streaming) -> sums per block of EMIT_GPB Gaussians
+constexpr uint32_t EMIT_GPB = 1024;  // Gaussians per count / emit block (four rounds of 256)
 __global__ void __launch_bounds__(256)
 count_rects_kernel(uint32_t N, const uint2 *__restrict__ rects_sorted, uint32_t *__restrict__ block_sums,
                    int32_t *__restrict__ start, int32_t *__restrict__ end, uint32_t n_tiles) {
   __shared__ uint32_t sm[8];
-  const uint32_t j = blockIdx.x * 256 + threadIdx.x;
-  for (uint32_t t = j; t < n_tiles; t += gridDim.x * 256) {  // aabb_culling.h:248-249 (instead of two memsets)
+  for (uint32_t t = blockIdx.x * 256 + threadIdx.x; t < n_tiles; t += gridDim.x * 256) {  // aabb_culling.h:248-249
     start[t] = -1;
     end[t] = -1;
   }
   uint32_t c = 0;
-  if (j < N) {
-    const uint32_t wh = rects_sorted[j].y;
-    c = (wh & 0xffffu) * (wh >> 16);
+#pragma unroll
+  for (uint32_t r = 0; r < EMIT_GPB / 256; ++r) {
+    const uint32_t j = blockIdx.x * EMIT_GPB + r * 256 + threadIdx.x;
+    if (j < N) {
+      const uint32_t wh = rects_sorted[j].y;
+      c += (wh & 0xffffu) * (wh >> 16);
+    }
   }
   uint32_t tot;
   block_exclusive_scan_256(c, sm, tot);
@@ -442,42 +444,59 @@ emit_rects_kernel(uint32_t N, uint32_t n_dub, uint32_t n_tiles_w, const uint32_t
   __shared__ uint32_t sm8[8];
   if (n_dev) n_dub = min(n_dub, *n_dev);
   const int lane = threadIdx.x & 31;
-  const uint32_t j = blockIdx.x * 256 + threadIdx.x;
-  uint32_t g = 0, c = 0, txy = 0, hh = 1;
-  if (j < N) {
-    g = ids_sorted[j];
-    const uint2 r = rects_sorted[j];
-    txy = r.x;
-    hh = r.y >> 16;
-    c = (r.y & 0xffffu) * hh;
-    if (hh == 0) hh = 1;
-  }
-  uint32_t tot;
-  const uint32_t excl = block_exclusive_scan_256(c, sm8, tot);
-  const uint32_t excl0 = __shfl_sync(0xffffffffu, excl, 0);
-  const uint32_t incl_w = excl + c - excl0;  // inclusive count within the warp
-  const uint32_t T = __shfl_sync(0xffffffffu, incl_w, 31);
-  const uint32_t wbase = block_offsets[blockIdx.x] + excl0;
-  for (uint32_t q0 = 0; q0 < T; q0 += 32) {
-    const uint32_t q = q0 + lane;
-    int s = 0;
+  uint32_t round_base = block_offsets[blockIdx.x];
+  for (uint32_t r = 0; r < EMIT_GPB / 256; ++r) {
+    const uint32_t j = blockIdx.x * EMIT_GPB + r * 256 + threadIdx.x;
+    uint32_t g = 0, c = 0, txy = 0, hh = 1;
+    if (j < N) {
+      g = ids_sorted[j];
+      const uint2 rc = rects_sorted[j];
+      txy = rc.x;
+      hh = rc.y >> 16;
+      c = (rc.y & 0xffffu) * hh;
+      if (hh == 0) hh = 1;
+    }
+    uint32_t tot;
+    if (r) __syncthreads();  // sm8 of the previous round has been read by everyone
+    const uint32_t excl = block_exclusive_scan_256(c, sm8, tot);
+    const uint32_t excl0 = __shfl_sync(0xffffffffu, excl, 0);
+    const uint32_t incl_w = excl + c - excl0;  // inclusive count within the warp
+    const uint32_t T = __shfl_sync(0xffffffffu, incl_w, 31);
+    const uint32_t wbase = round_base + excl0;
+    const float rh = __frcp_rn((float)hh);
+    for (uint32_t q0 = 0; q0 < T; q0 += 32) {
+      const uint32_t q = q0 + lane;
+      int s = 0;
 #pragma unroll
-    for (int step = 16; step > 0; step >>= 1) {
-      const uint32_t v = __shfl_sync(0xffffffffu, incl_w, s + step - 1);
-      if (v <= q) s += step;
+      for (int step = 16; step > 0; step >>= 1) {
+        const uint32_t v = __shfl_sync(0xffffffffu, incl_w, s + step - 1);
+        if (v <= q) s += step;
+      }
+      const uint32_t excl_s = __shfl_sync(0xffffffffu, incl_w - c, s);
+      const uint32_t txy_s = __shfl_sync(0xffffffffu, txy, s);
+      const uint32_t h_s = __shfl_sync(0xffffffffu, hh, s);
+      const float rh_s = __shfl_sync(0xffffffffu, rh, s);
+      const uint32_t g_s = __shfl_sync(0xffffffffu, g, s);
+      const uint32_t dest = wbase + q;
+      if (q < T && dest < n_dub) {  // never write past the caller's buffers
+        const uint32_t ql = q - excl_s;
+        // ql / h_s without the ~20-instruction integer division: float estimate + one correction step (exact
+        // below 2^22; larger rects -- > 4 M tiles under one Gaussian -- take the integer path)
+        uint32_t dx;
+        if (ql < (1u << 22)) {
+          dx = (uint32_t)((float)ql * rh_s);
+          const int rem = (int)(ql - dx * h_s);
+          dx += (rem >= (int)h_s) ? 1u : 0u;
+          dx -= (rem < 0) ? 1u : 0u;
+        } else {
+          dx = ql / h_s;
+        }
+        const uint32_t dy = ql - dx * h_s;
+        keys[dest] = ((txy_s >> 16) + dy) * n_tiles_w + (txy_s & 0xffffu) + dx;
+        vals[dest] = g_s;
+      }
     }
-    const uint32_t incl_s = __shfl_sync(0xffffffffu, incl_w, s);
-    const uint32_t c_s = __shfl_sync(0xffffffffu, c, s);
-    const uint32_t txy_s = __shfl_sync(0xffffffffu, txy, s);
-    const uint32_t h_s = __shfl_sync(0xffffffffu, hh, s);
-    const uint32_t g_s = __shfl_sync(0xffffffffu, g, s);
-    const uint32_t dest = wbase + q;
-    if (q < T && dest < n_dub) {  // never write past the caller's buffers
-      const uint32_t ql = q - (incl_s - c_s);
-      const uint32_t dx = ql / h_s, dy = ql - dx * h_s;
-      keys[dest] = ((txy_s >> 16) + dy) * n_tiles_w + (txy_s & 0xffffu) + dx;
-      vals[dest] = g_s;
-    }
+    round_base += tot;
   }
 }
 
@@ -903,9 +922,10 @@ static int binning_core(uint32_t N, uint32_t n_dub, uint32_t n_tiles_h, uint32_t
     if (rc) return rc;
   }
   // deterministic offsets: scan of the duplicate counts in depth order (+ start / end = -1)
-  count_rects_kernel<<<nb256, 256, 0, st>>>(N, rects, block_sums, start, end, n_tiles);
+  const uint32_t nb_emit = div_up(N, EMIT_GPB);
+  count_rects_kernel<<<nb_emit, 256, 0, st>>>(N, rects, block_sums, start, end, n_tiles);
   GS3D_LAUNCH_CHECK();
-  scan_block_sums_kernel<<<1, 1024, 0, st>>>(nb256, block_sums, total, n_dub, n_eff, n_dub_out_dev, overflow_dev);
+  scan_block_sums_kernel<<<1, 1024, 0, st>>>(nb_emit, block_sums, total, n_dub, n_eff, n_dub_out_dev, overflow_dev);
   GS3D_LAUNCH_CHECK();
   if (check_count && !device_count) {
     int64_t *box = pinned_mailbox();
@@ -921,7 +941,7 @@ static int binning_core(uint32_t N, uint32_t n_dub, uint32_t n_tiles_h, uint32_t
   uint32_t *vcur = (n_pass & 1) ? dV0 : ids_u;  // ping-pong so that the last pass lands in the caller's gaussian_ids
   uint32_t *vnext = (n_pass & 1) ? ids_u : dV0;
   uint32_t *kcur = dK0, *knext = dK1;
-  emit_rects_kernel<<<nb256, 256, 0, st>>>(N, n_dub, n_tiles_w, vB, rects, block_sums, kcur, vcur, n_eff);
+  emit_rects_kernel<<<nb_emit, 256, 0, st>>>(N, n_dub, n_tiles_w, vB, rects, block_sums, kcur, vcur, n_eff);
   GS3D_LAUNCH_CHECK();
   // tile-digit passes over the duplicates (high 32 bits of the reference key), bits split evenly
   int bits_pp = (tile_bits + n_pass - 1) / n_pass;
