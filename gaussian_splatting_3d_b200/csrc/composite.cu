@@ -571,11 +571,11 @@ __device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t byt
                : "memory");
 }
 // Blocking wait for the phase with the given parity.  One try_wait (the common case: the data is already there),
-// then a timed sleep between probes.  ncu history (profiles/): a bare try_wait loop spent 17 % of all issued
+// then a short sleep between probes.  History (profiles/): a bare try_wait loop spent 17 % of all issued
 // instructions probing; try_wait with a suspend-time hint compiles to TRYWAIT + NANOSLEEP.SYNCS, which wakes on
-// every mbarrier event of the SM -- 289 probes per blocked wait, 23 % of the kernel's instructions
-// (profiles/r2_ncu_bwd_ring_v2.txt).  A warp that has to wait is waiting for a slower warp of its tile, i.e. for
-// microseconds: a plain nanosleep of GS3D_WAIT_NS between probes costs it nothing and frees the issue slots.
+// every mbarrier event of the SM.  A warp that has to wait is waiting for a slower warp of its tile, i.e. for
+// microseconds; A/B of 100..1000 ns sleeps and of the hint form gave the same kernel time (the probes of a blocked
+// warp only use issue slots nobody else wants), so the simplest form stays.
 #ifndef GS3D_WAIT_NS
 #define GS3D_WAIT_NS 200u
 #endif
