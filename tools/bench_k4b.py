@@ -1,3 +1,8 @@
+"""K4b (projection backward) alone on the cfg-2 scene with three row filters: the frustum mask (dense), the
+compositing backward's touched marks through the one-thread-per-Gaussian kernel, and through the compacting kernel.
+
+    python tools/bench_k4b.py
+"""
 import sys, torch
 sys.path.insert(0, '/root/repo')
 from gaussian_splatting_3d_b200 import synthetic as S, parallel as P, ops
