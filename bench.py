@@ -51,6 +51,9 @@ def parse():
                          "NVLink/NVSwitch + small all-reduce; 'sparse' = all-reduce of the union of touched "
                          "rows only; 'allreduce' = one dense NCCL all-reduce; 'push' (= 'auto') = each rank "
                          "adds the rows it touched into every rank's result buffer over NVSwitch multicast")
+    ap.add_argument("--band-gather", default="root", choices=["root", "allgather"],
+                    help="cfg5, N>1: 'root' = bands stored straight into rank 0's frame over NVLink (symmetric "
+                         "memory); 'allgather' = every rank receives the full frame through one padded all_gather")
     ap.add_argument("--yaw-step", type=float, default=0.5,
                     help="N>1 (weak scaling, one view per rank): yaw between neighbouring ranks' poses in degrees.  "
                          "The cfg-2 scene covers the image with a 5 %% margin (about +-3.8 degrees of yaw): inside "
@@ -558,9 +561,13 @@ def run_cfg5(args, rank, local_rank, world, dev):
     c2w_dev = c2w_host.to(dev)
     frame_host = torch.empty(cam.h, cam.w, 3, dtype=torch.float32).pin_memory() if rank == 0 else None
 
+    # N > 1: the bands are composited straight into rank 0's frame buffer over NVLink (parallel.SharedFrame);
+    # `--band-gather allgather` selects the round-1 padded all_gather of the bands instead
+    shared = P.SharedFrame(cam, dev) if (world > 1 and args.band_gather == "root") else None
+
     def frame(e2e):
         c2w = c2w_host.to(dev, non_blocking=True) if e2e else c2w_dev
-        img = P.tile_sharded_render(r, c2w, cam)
+        img = P.tile_sharded_render(r, c2w, cam, frame=shared)
         if e2e and rank == 0:  # what the viewer does with a frame (viser_viewer.py:119-139: `.cpu()`)
             frame_host.copy_(img, non_blocking=True)
             torch.cuda.current_stream(dev).synchronize()
@@ -597,7 +604,7 @@ def run_cfg5(args, rank, local_rank, world, dev):
     full = frame(False)
     with torch.no_grad():
         ref_img = r(c2w_dev, cam)
-    shard_err = float((full - ref_img).abs().max())
+    shard_err = float((full - ref_img).abs().max()) if full is not None else None  # (root only with SharedFrame)
     n_dub = r.total_dub_gaussians
     line = {
         "metric": "forward FPS (6M Gaussians SH3 @3840x2160, tile rows sharded)", "value": 1000.0 * args.steps / ms,
@@ -606,7 +613,10 @@ def run_cfg5(args, rank, local_rank, world, dev):
         "dtype": "f32", "data": "synthetic",
         "config": {"workload": workload_desc(name, r.N, C, cam, 1), "n_dub": n_dub, "views_per_step": 1,
                    "parallelism": f"tiles{world}" if world > 1 else "single"},
-        "impl_details": {"sharding": f"tile rows sharded over {world} rank(s), bands gathered on every rank",
+        "impl_details": {"sharding": (f"tile rows sharded over {world} rank(s); " +
+                                      ("bands stored straight into rank 0's frame buffer over NVLink (symmetric "
+                                       "memory, two barriers per frame)" if shared is not None else
+                                       "bands gathered on every rank (padded all_gather)")),
                          "l2_policy": "inputs larger than L2 (parameters 1.4 GB, duplicates 1 GB vs 126 MB L2)",
                          "exact_decisions": not args.no_exact},
         "sharded_vs_single_gpu_max_abs": shard_err,

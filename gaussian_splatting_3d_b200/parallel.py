@@ -436,7 +436,7 @@ def clip_rects_to_band(aabb_topleft, aabb_bottomright, row_begin, row_end):
 
 
 @torch.no_grad()
-def render_band(renderer, c2w, camera_info, row_begin=None, row_end=None, k1=None):
+def render_band(renderer, c2w, camera_info, row_begin=None, row_end=None, k1=None, out=None):
     """Forward-render tile rows [row_begin, row_end) of one frame (None = all rows).  Returns the
     full-size [H,W,3] buffer in which only the band's rows are DEFINED (the rest is uninitialised memory), plus
     the K1 outputs."""
@@ -467,7 +467,10 @@ def render_band(renderer, c2w, camera_info, row_begin=None, row_end=None, k1=Non
         ids = torch.index_select(index, 0, ids)
     # only the band's rows are ever read back: empty tiles of the band keep the zero fill, the rest of the
     # full-size buffer stays uninitialised (a 4K frame is 99.5 MB: no full fill per band)
-    out = torch.empty(H * W * 3, dtype=torch.float32, device=dev)
+    # `out` may be another rank's frame buffer mapped into this process (symmetric memory): the compositing kernel
+    # then stores the band's pixels straight over NVLink
+    if out is None:
+        out = torch.empty(H * W * 3, dtype=torch.float32, device=dev)
     out[row_begin * tile * W * 3: min(row_end * tile, H) * W * 3].zero_()
     topleft = renderer._topleft(cam) if hasattr(renderer, "_topleft") else \
         torch.tensor([-cam.cx / cam.fx, -cam.cy / cam.fy], dtype=torch.float32).to(dev)
@@ -478,10 +481,35 @@ def render_band(renderer, c2w, camera_info, row_begin=None, row_end=None, k1=Non
     return out.view(H, W, 3), k1
 
 
+class SharedFrame:
+    """A frame buffer on `root` that every rank of the group can store into: torch symmetric memory, each
+    rank holds a tensor view of the ROOT's buffer (peer mapping over NVLink).  tile_sharded_render(frame=...)
+    composites every band straight into it -- no gather step, no staging copies; two symmetric-memory barriers
+    per frame order 'root is done with the previous frame' -> stores -> 'all bands have landed'."""
+
+    def __init__(self, camera_info, device, group=None, root=0):
+        import torch.distributed._symmetric_memory as symm_mem
+
+        grp = group if group is not None else dist.group.WORLD
+        n = camera_info.h * camera_info.w * 3
+        self.local = symm_mem.empty(n, dtype=torch.float32, device=device)
+        self.handle = symm_mem.rendezvous(self.local, grp)
+        self.root = root
+        self.rank = dist.get_rank(group)
+        self.shape = (camera_info.h, camera_info.w, 3)
+        self.root_view = self.local if self.rank == root else self.handle.get_buffer(root, (n,), torch.float32)
+
+    def image(self):
+        """The finished frame ([H,W,3]) on the root, None elsewhere."""
+        return self.local.view(self.shape) if self.rank == self.root else None
+
+
 @torch.no_grad()
-def tile_sharded_render(renderer, c2w, camera_info, group=None, gather=True):
+def tile_sharded_render(renderer, c2w, camera_info, group=None, gather=True, frame=None):
     """Render one frame with tile rows sharded over the ranks of `group` (forward only).
-    Every rank returns the full [H,W,3] image when gather=True, else (its band [rows,W,3], row0)."""
+    frame=None: every rank returns the full [H,W,3] image when gather=True (one padded all_gather), else (its band
+    [rows,W,3], row0).  frame=SharedFrame: the bands are composited straight into the root's frame buffer over
+    NVLink; returns frame.image() (the full frame on the root, None elsewhere)."""
     from . import ops
 
     rank = dist.get_rank(group) if dist.is_initialized() else 0
@@ -498,6 +526,11 @@ def tile_sharded_render(renderer, c2w, camera_info, group=None, gather=True):
         sync_count=False, want_projection=False)  # (the whole-frame duplicate count is not needed here)
     bands = balanced_bands(row_duplicate_counts(k1["tl"], k1["br"], nth), world)
     r0, r1 = bands[rank]
+    if frame is not None and world > 1:
+        frame.handle.barrier(channel=0)  # the root has consumed the previous frame (stream order on the root)
+        render_band(renderer, c2w, cam, r0, r1, k1=k1, out=frame.root_view)
+        frame.handle.barrier(channel=0)  # every band has landed in the root's buffer
+        return frame.image()
     img, _ = render_band(renderer, c2w, cam, r0, r1, k1=k1)
     y0, y1 = r0 * tile, min(r1 * tile, H)
     if world == 1:

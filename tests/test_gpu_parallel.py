@@ -59,6 +59,15 @@ def _worker(rank, world, port, q):
     with torch.no_grad():
         single = r(c2w, cam)
     ok_render = bool(torch.equal(full, single))
+    # same frame with the bands stored straight into rank 0's frame buffer (symmetric memory, no gather step);
+    # twice: the second frame must wait until the root is done with the first
+    shared = P.SharedFrame(cam, dev)
+    for _ in range(2):
+        img = P.tile_sharded_render(r, c2w, cam, frame=shared)
+        if rank == 0:
+            ok_render = ok_render and bool(torch.equal(img, single))
+        else:
+            ok_render = ok_render and img is None
     # view-sharded step over 4 cameras
     import math
     c2ws = []
