@@ -407,7 +407,7 @@ def run_ours(args, rank, local_rank, world):
             ms_e2e = timed(lambda: step(True), args.steps)
             if sync_free_capacity is not None:
                 assert not r.overflowed(), "static capacity overflowed during the timed steps"
-            launches = launches_per_step * args.steps  # kernels executed in the timed region (graph nodes included)
+        launches = launches_per_step * args.steps  # kernels executed in the timed region (graph nodes included)
     clocks = clk.summary()
     for _ in range(2):  # (graph capture emptied the allocator cache: refill it before the per-stage event timing)
         step(False)
