@@ -973,7 +973,10 @@ static size_t bwd3_smem() {
          (size_t)2 * RS * sizeof(unsigned long long);
 }
 
-constexpr int FWD_B = 64;
+#ifndef GS3D_FWD_B
+#define GS3D_FWD_B 64
+#endif
+constexpr int FWD_B = GS3D_FWD_B;  // (A/B, cfg 2: 32 / 64 / 128 Gaussians per batch x 3..6 CTAs per SM: 64 x 4 is fastest)
 
 template <int C, int B, bool EXACT, bool RGB, bool STATS>
 static int launch_fwd_t(const CompositeParams &p, uint32_t n_tiles, cudaStream_t st) {
