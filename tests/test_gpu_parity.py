@@ -9,11 +9,15 @@ max-abs; gradients <= 1e-3 relative.  A skip decision (alpha*G vs 1/255) that fl
 expf is glibc's, not CUDA's) are made on the pixels whose decisions are FP-stable (oracle margin
 diagnostic) and the number of fragile pixels is bounded separately.
 """
+from pathlib import Path
+
 import numpy as np
 import pytest
 import torch
 
 from gaussian_splatting_3d_b200 import synthetic as S
+
+ROOT = Path(__file__).resolve().parent.parent
 
 pytestmark = pytest.mark.gpu
 
@@ -440,3 +444,85 @@ def test_cfg2_full_size_properties(ops):
     area = ((br[:, 0] - tl[:, 0] + 1) * (br[:, 1] - tl[:, 1] + 1)).long() * mask.long()
     assert int(area.sum()) == n_dub
     assert torch.equal(torch.bincount(ids1.long(), minlength=r.N), area)
+
+
+# ---------------------------------------------------------------- round-2 kernels against their own dense forms
+def test_projection_backward_sparse_filter_equals_dense(ops):
+    """K4b with the compositing backward's `touched` marks as a sparse row filter (compacting kernel, accumulate
+    == 2) == the one-thread-per-Gaussian kernel over the frustum mask, on the same upstream 2-D gradients: the
+    unmarked rows carry zero gradients, so both add the same values to the same rows."""
+    cam = S.make_camera("cfg1")
+    sc = S.make_scene("cfg1", seed=5, N=30_001)  # (not a multiple of 16 / 512: exercises the tail of the mark scan)
+    N = sc["mean"].shape[0]
+    p = {k: sc[k].to(DEV) for k in ("mean", "qvec", "svec_before_activation", "alpha_before_activation")}
+    c2w = sc["c2w"].to(DEV)
+    g = torch.Generator(device=DEV).manual_seed(3)
+    marks = (torch.rand(N, device=DEV, generator=g) < 0.03).to(torch.uint8)
+    frustum = torch.ones(N, dtype=torch.bool, device=DEV)
+    m = marks.bool()
+    gm2 = torch.zeros(N, 2, device=DEV); gcov = torch.zeros(N, 4, device=DEV); ga = torch.zeros(N, device=DEV)
+    gm2[m] = torch.randn(int(m.sum()), 2, device=DEV, generator=g)
+    gcov[m] = torch.randn(int(m.sum()), 4, device=DEV, generator=g)
+    ga[m] = torch.randn(int(m.sum()), device=DEV, generator=g)
+    outs = []
+    for mask, sparse in ((frustum, False), (marks, True)):
+        leaf = (torch.full((N, 3), 0.5, device=DEV), torch.full((N, 4), 0.25, device=DEV),
+                torch.full((N, 3), -1.0, device=DEV), torch.full((N,), 2.0, device=DEV))
+        acc = torch.zeros(N, device=DEV)
+        ops.project_backward_fused(mask, p["mean"], p["qvec"], p["svec_before_activation"],
+                                   p["alpha_before_activation"], 1, 1, c2w, True, gm2, gcov, ga, grad_mean_acc=acc,
+                                   adc_mode=2, out=leaf, accumulate=True, sparse_filter=sparse)
+        outs.append(leaf + (acc,))
+    for a, b in zip(*outs):
+        assert torch.equal(a, b)
+    assert float((outs[1][0][~m] - 0.5).abs().max()) == 0.0  # unmarked rows untouched
+
+
+def test_binning_specialised_passes_equal_round1_pipeline(tmp_path):
+    """The specialised radix passes (binning.cu: first / last depth pass, packed rects, fused ranges) against the
+    round-1 three-kernel pipeline (GS3D_SORT=classic, read once per process -> subprocesses): identical ids,
+    start and end, in exact-count and in capacity mode."""
+    import os
+    import subprocess
+    import sys
+
+    script = r"""
+import sys, torch
+sys.path.insert(0, %r)
+from gaussian_splatting_3d_b200 import ops, synthetic as S
+dev = 'cuda:0'
+cam = S.make_camera('cfg3'); sc = S.make_scene('cfg3', seed=2, N=200_003)
+d = {k: v.to(dev) for k, v in sc.items() if torch.is_tensor(v)}
+k1 = ops.project_cull_fused(d['mean'], d['qvec'], d['svec_before_activation'], d['alpha_before_activation'], 1, 1,
+                            d['c2w'], cam, 1.0, False, 6.0, 16)
+n = k1['n_dub']; nth, ntw = (cam.h + 15) // 16, (cam.w + 15) // 16
+res = {}
+ids = torch.empty(n, dtype=torch.int32, device=dev)
+st = torch.empty(nth * ntw, dtype=torch.int32, device=dev); en = torch.empty_like(st)
+keys = torch.empty(n, dtype=torch.int64, device=dev)
+ops.tile_culling_aabb_start_end(k1['tl'], k1['br'], ids, st, en, k1['depth'], nth, ntw, sorted_keys=keys)
+res['exact'] = [t.cpu() for t in (ids, st, en, keys)]
+cap = n + 12345
+ids2 = torch.full((cap,), -7, dtype=torch.int32, device=dev)
+nd, ov = ops.tile_culling_aabb_start_end_capacity(k1['tl'], k1['br'], ids2, st, en, k1['depth'], nth, ntw)
+res['capacity'] = [ids2[:n].cpu(), st.cpu(), en.cpu(), nd.cpu(), ov.cpu()]
+small = n // 3
+ids3 = torch.empty(small, dtype=torch.int32, device=dev)
+nd, ov = ops.tile_culling_aabb_start_end_capacity(k1['tl'], k1['br'], ids3, st, en, k1['depth'], nth, ntw)
+res['overflow'] = [ids3.cpu(), st.cpu(), en.cpu(), nd.cpu(), ov.cpu()]
+torch.save(res, sys.argv[1])
+""" % str(ROOT)
+    outs = {}
+    for mode in ("new", "classic"):
+        env = dict(os.environ)
+        env.pop("GS3D_SORT", None)
+        if mode == "classic":
+            env["GS3D_SORT"] = "classic"
+        f = tmp_path / f"{mode}.pt"
+        r = subprocess.run([sys.executable, "-c", script, str(f)], env=env, capture_output=True, text=True, timeout=600)
+        assert r.returncode == 0, r.stderr[-2000:]
+        outs[mode] = torch.load(f)
+    for case in ("exact", "capacity", "overflow"):
+        for a, b in zip(outs["new"][case], outs["classic"][case]):
+            assert torch.equal(a, b), case
+    assert int(outs["new"]["overflow"][4]) == 1 and int(outs["new"]["capacity"][4]) == 0

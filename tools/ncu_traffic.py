@@ -50,7 +50,7 @@ def main():
     hdr, units = rows[0], rows[1]
     col = {h: i for i, h in enumerate(hdr)}
     scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "usecond": 1e-3, "msecond": 1.0, "nsecond": 1e-6,
-             "second": 1e3}
+             "second": 1e3, "ns": 1e-6, "us": 1e-3, "ms": 1.0, "s": 1e3}
 
     def val(r, name):
         i = col.get(name)
