@@ -502,7 +502,7 @@ def run_ours(args, rank, local_rank, world):
                                              "only the rows the previous backward marked",
                          "l2_policy": "inputs larger than L2 (parameters 708 MB, duplicates 132 MB vs 126 MB L2)",
                          "exact_decisions": not args.no_exact,
-                         "step_launch": ("2 CUDA-graph launches per step (graph.GraphedStep: static capacity "
+                         "step_launch": ("3 CUDA-graph launches per step ([reset + forward], [loss], [backward]; graph.GraphedStep: static capacity "
                                          f"{gstep.capacity} duplicates, no host round trip)" if gstep is not None
                                          else ("eager launches, static duplicate capacity "
                                                f"{sync_free_capacity} (no host round trip in the step)"

@@ -1,6 +1,8 @@
 """A whole training step -- gradient reset, forward (cull + project + bin + composite), loss, backward to the
-leaf parameters -- captured once in two CUDA graphs ([reset + forward], [loss + backward]) and replayed with two
-launches per step.
+leaf parameters -- captured once in three CUDA graphs ([reset + forward], [loss], [backward]) and replayed with
+three launches per step.  The loss graph is separate so that the step's result (loss + overflow flag, 8 bytes) can
+be copied to the host as soon as it exists: a caller that reads the loss every step gets it while the backward
+kernels (more than half of the step) still run, and has the next step enqueued before the GPU goes idle.
 
 The reference's step has three host synchronisations inside the forward alone (boolean-mask `nonzero`,
 `.item()` in gs/culling.py:33-35, the D2H memcpy + cudaFree in aabb_culling.h:204-259) and ~250 kernel
@@ -30,12 +32,14 @@ class GraphedStep:
         self.margin = margin
         self.warmup = warmup
         self.loss_fn = loss_fn or (lambda out, tgt: ((out - tgt) ** 2).mean())
-        self.g_fwd = self.g_bwd = None  # two graphs: the target image is only needed by the second
+        self.g_fwd = self.g_loss = self.g_bwd = None  # (the target image is first needed by the loss graph)
         dev = renderer.mean.device
         self.c2w = torch.zeros(3, 4, dtype=torch.float32, device=dev)
         self.target = torch.zeros(camera_info.h, camera_info.w, 3, dtype=torch.float32, device=dev)
         self.loss = None
         self.status = None  # [loss, overflow flag] packed for one 8-byte read-back
+        self._status_host = torch.zeros(2, dtype=torch.float32).pin_memory()
+        self._status_ready = torch.cuda.Event()
         self._copy_stream = torch.cuda.Stream(device=dev)
 
     # ------------------------------------------------------------------ capture
@@ -69,16 +73,20 @@ class GraphedStep:
                 self._body()
         torch.cuda.current_stream(dev).wait_stream(s)
         torch.cuda.synchronize(dev)
-        # Two graphs sharing one memory pool: [reset + forward] and [loss + backward].  The target image is first
-        # read by the loss, so its host->device copy (13 MB at cfg 2) overlaps the forward graph.
+        # Three graphs sharing one memory pool: [reset + forward], [loss], [backward].  The target image is first
+        # read by the loss, so its host->device copy (13 MB at cfg 2) overlaps the forward graph; the loss and the
+        # overflow flag are final before the backward starts, so their read-back overlaps the backward graph.
         self.g_fwd = torch.cuda.CUDAGraph()
         with torch.cuda.graph(self.g_fwd):
             out = self._forward()
-        self.g_bwd = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(self.g_bwd, pool=self.g_fwd.pool()):
-            loss = self._backward(out)
+        self.g_loss = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.g_loss, pool=self.g_fwd.pool()):
+            loss = self.loss_fn(out, self.target)
             self.loss = loss.detach()
             self.status = torch.stack([self.loss.reshape(()), r._overflow.reshape(()).to(torch.float32)])
+        self.g_bwd = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.g_bwd, pool=self.g_fwd.pool()):
+            self.flat.backward_into(loss)
         self.out = out
         # the capture leaves the parameters' .grad aliased to the flat buffer's views, as the eager step does
 
@@ -104,9 +112,14 @@ class GraphedStep:
         self.g_fwd.replay()
         if side:
             main.wait_stream(self._copy_stream)
+        self.g_loss.replay()
+        if read_loss:  # 8 bytes to pinned memory, enqueued BEFORE the backward graph
+            self._status_host.copy_(self.status, non_blocking=True)
+            self._status_ready.record(main)
         self.g_bwd.replay()
         if read_loss:
-            st = self.status.tolist()  # one D2H read of [loss, overflow]
+            self._status_ready.synchronize()  # the loss is on the host; the backward is still running
+            st = self._status_host.tolist()
             if st[1] != 0.0:
                 raise RuntimeError(f"GraphedStep: the duplicate count exceeded the static capacity {self.capacity}; "
                                    "re-create the step with a larger capacity")
