@@ -303,6 +303,8 @@ def run_ours(args, rank, local_rank, world):
                                pull=(mode == "pull")).attach(r)
 
     copy_stream = torch.cuda.Stream(device=dev)
+    loss_host = torch.zeros(1, dtype=torch.float32).pin_memory()
+    loss_ready = torch.cuda.Event()
 
     def step(e2e):
         flat.zero()  # per-step reset of the gradient buffers (N > 1: side stream, overlaps the forward)
@@ -326,14 +328,20 @@ def run_ours(args, rank, local_rank, world):
             if tgt_ready is not None:
                 torch.cuda.current_stream(dev).wait_event(tgt_ready)
             loss = ((out - tgt) ** 2).mean()
-            flat.backward_into(loss)  # accumulates into the flat buffer
             total = loss.detach() if total is None else total + loss.detach()
+            if e2e and v == len(c2w_devs) - 1:
+                # the step's result is final once the last view's loss exists: its 4-byte device -> host copy is
+                # enqueued BEFORE that view's backward (and the exchange), so the host has it while they still run
+                loss_host.copy_(total.reshape(1), non_blocking=True)
+                loss_ready.record(torch.cuda.current_stream(dev))
+            flat.backward_into(loss)  # accumulates into the flat buffer
         if world > 1:
             flat.exchange()
             if cfg4:  # a training step: the ADC statistics follow the gradients (parallel.view_sharded_step)
                 P.sync_adc(r)
         if e2e:
-            return float(total.item())  # device -> host read of the step's result
+            loss_ready.synchronize()
+            return float(loss_host[0])  # device -> host read of the step's result
         return total
 
     def fwd_only():
