@@ -703,13 +703,16 @@ def stage_rooflines(kernels_ms, N, C, cam, n_dub, views, staged, pairs, ncu_ok, 
             ncu = {}
     out = {}
     meta = ncu.get("_meta") or {}
-    if meta.get("lib_sha256_16"):  # was the committed ncu capture taken from the library that is loaded now?
+    if meta.get("src_sha256_16"):  # was the committed ncu capture taken from the kernel sources that are built now?
         import hashlib
 
-        lib = ROOT / "gaussian_splatting_3d_b200" / "libgs3d_b200.so"
-        now = hashlib.sha256(lib.read_bytes()).hexdigest()[:16] if lib.exists() else None
-        out["_ncu_capture"] = {"lib_sha256_16": meta["lib_sha256_16"], "loaded_lib_sha256_16": now,
-                               "same_build": now == meta["lib_sha256_16"], "capture": meta.get("capture")}
+        h = hashlib.sha256()
+        for f in sorted((ROOT / "gaussian_splatting_3d_b200" / "csrc").glob("*.cu*")) + [ROOT / "include" / "gs3d_b200.h"]:
+            h.update(f.name.encode())
+            h.update(f.read_bytes())
+        now = h.hexdigest()[:16]
+        out["_ncu_capture"] = {"src_sha256_16": meta["src_sha256_16"], "current_src_sha256_16": now,
+                               "same_sources": now == meta["src_sha256_16"], "capture": meta.get("capture")}
     for k, ms in kernels_ms.items():
         if k not in algo or ms <= 0:
             continue

@@ -31,6 +31,17 @@ UTIL = {"issue_slot_pct": "smsp__issue_active.avg.pct_of_peak_sustained_active",
         "dram_pct": "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed"}
 
 
+def source_hash():
+    """Hash of the kernel sources the library is built from (csrc/*.cu, *.cuh, the C header): stable across
+    rebuilds, unlike the .so (nvcc output is not byte-reproducible)."""
+    h = hashlib.sha256()
+    files = sorted((ROOT / "gaussian_splatting_3d_b200" / "csrc").glob("*.cu*")) + [ROOT / "include" / "gs3d_b200.h"]
+    for f in files:
+        h.update(f.name.encode())
+        h.update(f.read_bytes())
+    return h.hexdigest()[:16]
+
+
 def num(x):
     try:
         return float(x.replace(",", ""))
@@ -75,9 +86,8 @@ def main():
         d["launches"] += 1
         if t > d["_top"][0]:
             d["_top"] = (t, r)
-    lib = ROOT / "gaussian_splatting_3d_b200" / "libgs3d_b200.so"
-    sha = hashlib.sha256(lib.read_bytes()).hexdigest()[:16] if lib.exists() else None
-    res = {"_meta": {"capture": rep, "note": note, "lib_sha256_16": sha,
+    sha = source_hash()
+    res = {"_meta": {"capture": rep, "note": note, "src_sha256_16": sha,
                      "method": "ncu --set full --clock-control none, one eager cfg-2 step (tools/one_step.py); "
                                "cold-cache serialised replays: bytes are per stage per step, times are NOT bench times"}}
     for st, d in stages.items():
