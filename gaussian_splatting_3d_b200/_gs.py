@@ -141,15 +141,62 @@ def _legacy(name, instead):
     return fn
 
 
+def _ranges_from_offset(offset):
+    """CSR offsets [n_tiles + 1] of the deprecated bindings -> (start, end) with -1 for empty tiles."""
+    ops._chk(offset, "offset", torch.int32)
+    start, end = offset[:-1].clone(), offset[1:].clone()
+    empty = start >= end
+    start[empty] = -1
+    end[empty] = -1
+    return start, end
+
+
+def tile_based_vol_rendering(mean, cov, color, alpha, offset, gaussian_ids, out, topleft, tile_size, n_tiles_h,
+                             n_tiles_w, pixel_size_x, pixel_size_y, H, W, thresh):
+    """bindings.cpp:15 -> render.cu:178-217 (vol_render.h:354-412): the CSR-`offset` form of the RGB compositing
+    (tile t owns gaussian_ids[offset[t]:offset[t+1]]); same per-pixel arithmetic as the start/end form
+    (vol_render_one_batch, vol_render.h:252-352), so it runs on the same kernel."""
+    start, end = _ranges_from_offset(offset)
+    tile_based_vol_rendering_start_end(mean, cov, color, alpha, start, end, gaussian_ids, out, topleft, tile_size,
+                                       n_tiles_h, n_tiles_w, pixel_size_x, pixel_size_y, H, W, thresh)
+
+
+# bindings.cpp:22,25: the v1 / v2 kernels differ from v0 in their shared-memory staging only (vol_render.h:414-640)
+tile_based_vol_rendering_v1 = tile_based_vol_rendering
+tile_based_vol_rendering_v2 = tile_based_vol_rendering
+
+
+def tile_based_vol_rendering_backward(mean, cov, color, alpha, offset, gaussian_ids, out, grad_mean, grad_cov,
+                                      grad_color, grad_alpha, grad_out, topleft, tile_size, n_tiles_h, n_tiles_w,
+                                      pixel_size_x, pixel_size_y, H, W, thresh):
+    """bindings.cpp:17 -> render.cu:303-360: backward of the CSR-`offset` form."""
+    start, end = _ranges_from_offset(offset)
+    tile_based_vol_rendering_backward_start_end(mean, cov, color, alpha, start, end, gaussian_ids, out, grad_mean,
+                                                grad_cov, grad_color, grad_alpha, grad_out, topleft, tile_size,
+                                                n_tiles_h, n_tiles_w, pixel_size_x, pixel_size_y, H, W, thresh)
+
+
+def tile_culling_aabb(aabb_topleft, aabb_bottomright, gaussian_ids, offset, depth, n_tiles_h, n_tiles_w):
+    """bindings.cpp:21 -> render.cu:362-378 (aabb_culling.h:105-190): binning into the CSR-`offset` form.  The
+    reference leaves the offsets of blank tiles unwritten (aabb_culling.h:178-182, the reason the form is
+    deprecated); here offset is the proper exclusive scan of the per-tile counts, offset[n_tiles] = N_with_dub."""
+    ops._chk(offset, "offset", torch.int32)
+    n_tiles = int(n_tiles_h) * int(n_tiles_w)
+    if offset.numel() != n_tiles + 1:
+        raise RuntimeError("offset must have n_tiles_h * n_tiles_w + 1 elements")
+    start = torch.empty(n_tiles, dtype=torch.int32, device=depth.device)
+    end = torch.empty_like(start)
+    ops.tile_culling_aabb_start_end(aabb_topleft, aabb_bottomright, gaussian_ids, start, end, depth,
+                                    n_tiles_h, n_tiles_w)
+    counts = (end - start).clamp_(min=0)  # (-1) - (-1) = 0 for blank tiles
+    offset[0] = 0
+    torch.cumsum(counts, 0, out=offset[1:])
+
+
 count_num_gaussians_each_tile = _legacy("count_num_gaussians_each_tile", "gs.culling.tile_culling_aabb_count")
 count_num_gaussians_each_tile_bcircle = _legacy("count_num_gaussians_each_tile_bcircle", "gs.culling.tile_culling_aabb_count")
 prepare_image_sort = _legacy("prepare_image_sort", "tile_culling_aabb_start_end")
 image_sort = _legacy("image_sort", "tile_culling_aabb_start_end")
-tile_culling_aabb = _legacy("tile_culling_aabb", "tile_culling_aabb_start_end")
-tile_based_vol_rendering = _legacy("tile_based_vol_rendering", "tile_based_vol_rendering_start_end")
-tile_based_vol_rendering_v1 = _legacy("tile_based_vol_rendering_v1", "tile_based_vol_rendering_start_end")
-tile_based_vol_rendering_v2 = _legacy("tile_based_vol_rendering_v2", "tile_based_vol_rendering_start_end")
-tile_based_vol_rendering_backward = _legacy("tile_based_vol_rendering_backward", "tile_based_vol_rendering_backward_start_end")
 # the two experimental backward variants compute the same gradients as the main one
 tile_based_vol_rendering_backward_sh_v1 = tile_based_vol_rendering_backward_sh
 tile_based_vol_rendering_backward_sh_warp_reduce = tile_based_vol_rendering_backward_sh
