@@ -589,6 +589,11 @@ __device__ __forceinline__ bool mbar_try(uint32_t bar, uint32_t parity) {
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, uint32_t sleep_ns = GS3D_WAIT_NS) {
   while (!mbar_try(bar, parity)) __nanosleep(sleep_ns);
 }
+// Arrival on `bar` that fires when all cp.async copies this thread has issued so far have landed (the pending count is
+// NOT incremented: the barrier must have been initialised with this arrival counted in)
+__device__ __forceinline__ void cp_async_arrive_noinc(uint32_t bar) {
+  asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(bar) : "memory");
+}
 // 1-D bulk copy global -> shared (TMA engine, UBLKCP); bytes is a multiple of 16, both addresses 16-byte aligned
 __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
@@ -753,10 +758,13 @@ composite_bwd3_kernel(const CompositeParams p) {
   const int n_batches = (n_this + RG - 1) / RG;
   const uint32_t bar_full = smem_u32(s_bar), bar_done = smem_u32(s_bar + RS);
 
+  // bulk staging (16-byte addressable SH rows): ONE arrival (+ the copies' byte count) completes `full`; element-wise
+  // staging: every producer lane arrives, asynchronously, when its own cp.async copies have landed
+  const bool bulk = RGB ? false : (p.sh_vec != 0);
   if (threadIdx.x == 0) {
 #pragma unroll
     for (int s2 = 0; s2 < RS; ++s2) {
-      mbar_init(bar_full + 8 * s2, 1);
+      mbar_init(bar_full + 8 * s2, bulk ? 1 : 32);
       mbar_init(bar_done + 8 * s2, NW);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -772,10 +780,9 @@ composite_bwd3_kernel(const CompositeParams p) {
       const int s2 = t & (RS - 1);
       if (t > end_b) return;
       if (t == end_b) {  // sentinel: no Gaussians
-        if (lane == 0) {
-          s_nvalid[s2] = 0;
-          mbar_arrive(bar_full + 8 * s2);
-        }
+        if (lane == 0) s_nvalid[s2] = 0;
+        __syncwarp();
+        if (bulk ? lane == 0 : true) mbar_arrive(bar_full + 8 * s2);
         return;
       }
       asm volatile("cp.async.wait_all;" ::: "memory");  // this warp's own id prefetches have landed
@@ -797,7 +804,6 @@ composite_bwd3_kernel(const CompositeParams p) {
         s_rec[s2 * RG * 3 + e] = (e % 3 == 0) ? make_float4(0.f, 0.f, 0.f, __int_as_float(0x7f800000))
                                               : make_float4(0.f, 0.f, 0.f, 0.f);
       }
-      const bool bulk = RGB ? false : (p.sh_vec != 0);
       if (bulk) {
         const bool dense = p.sh_sc == (uint32_t)CC;
         const uint32_t sh_bytes = 4 * SHF;
@@ -820,8 +826,10 @@ composite_bwd3_kernel(const CompositeParams p) {
           }
         }
       } else {
-        // element-wise staging (SH rows that are not 16-byte addressable, RGB colours): this warp can afford to
-        // wait for its copies -- nobody waits for IT unless the whole ring has run dry
+        // element-wise staging (SH rows that are not 16-byte addressable, RGB colours): every lane arrives on `full`
+        // when ITS copies have landed (cp.async.mbarrier.arrive), so the warp does not wait for them and goes
+        // straight back to flushing; the plain stores above (padding, s_nvalid) are fenced before the arrivals
+        if (lane == 0) s_nvalid[s2] = nv;
         for (int e = lane; e < nv * 3; e += 32)
           cp_async_16(s_rec + s2 * RG * 3 + e, p.records + 3 * (size_t)idp[e / 3] + (e % 3));
         for (int e = lane; e < nv * SHF; e += 32) {
@@ -829,13 +837,8 @@ composite_bwd3_kernel(const CompositeParams p) {
           const int c = r / CC, k = r - c * CC;
           cp_async_4(s_sh + (s2 * RG + j) * SHF + r, p.sh + (size_t)idp[j] * p.sh_sg + c * p.sh_sc + k);
         }
-        asm volatile("cp.async.wait_all;" ::: "memory");
         __threadfence_block();
-        __syncwarp();
-        if (lane == 0) {
-          s_nvalid[s2] = nv;
-          mbar_arrive(bar_full + 8 * s2);
-        }
+        cp_async_arrive_noinc(bar_full + 8 * s2);
       }
       staged += (unsigned long long)nv;
     };
