@@ -303,6 +303,8 @@ def run_ours(args, rank, local_rank, world):
                                pull=(mode == "pull")).attach(r)
 
     copy_stream = torch.cuda.Stream(device=dev)
+    c2w_stage = [torch.empty_like(c) for c in c2w_devs]  # device staging buffers of the end-to-end path
+    tgt_stage = [torch.empty_like(t) for t in tgt_devs]
     loss_host = torch.zeros(1, dtype=torch.float32).pin_memory()
     loss_ready = torch.cuda.Event()
 
@@ -313,15 +315,17 @@ def run_ours(args, rank, local_rank, world):
             tgt_ready = None
             if e2e:
                 # the pose (48 B) is needed by the first kernel: current stream.  The 13 MB target image is not
-                # needed before the loss: its host->device copy runs on a copy stream beside the forward kernels
-                c2w = c2w_hosts[v].to(dev, non_blocking=True)
+                # needed before the loss: its host->device copy runs on a copy stream beside the forward kernels.
+                # Both land in persistent staging buffers (no allocation, no record_stream bookkeeping per step).
+                c2w = c2w_stage[v]
+                c2w.copy_(c2w_hosts[v], non_blocking=True)
                 main = torch.cuda.current_stream(dev)
-                copy_stream.wait_stream(main)  # (the previous consumers of the recycled block are done)
+                copy_stream.wait_stream(main)  # (the previous step's loss has read this staging buffer)
                 with torch.cuda.stream(copy_stream):
-                    tgt = tgt_hosts[v].to(dev, non_blocking=True)
+                    tgt = tgt_stage[v]
+                    tgt.copy_(tgt_hosts[v], non_blocking=True)
                     tgt_ready = torch.cuda.Event()
                     tgt_ready.record(copy_stream)
-                tgt.record_stream(main)
             else:
                 c2w, tgt = c2w_devs[v], tgt_devs[v]
             out = r(c2w, cam)
@@ -329,9 +333,9 @@ def run_ours(args, rank, local_rank, world):
                 torch.cuda.current_stream(dev).wait_event(tgt_ready)
             loss = ((out - tgt) ** 2).mean()
             total = loss.detach() if total is None else total + loss.detach()
-            if e2e and v == len(c2w_devs) - 1:
-                # the step's result is final once the last view's loss exists: its 4-byte device -> host copy is
-                # enqueued BEFORE that view's backward (and the exchange), so the host has it while they still run
+            if e2e and len(c2w_devs) == 1:
+                # one view per step: the step's result is final once the loss exists: its 4-byte device -> host copy
+                # is enqueued BEFORE the backward (and the exchange), so the host has it while they still run
                 loss_host.copy_(total.reshape(1), non_blocking=True)
                 loss_ready.record(torch.cuda.current_stream(dev))
             flat.backward_into(loss)  # accumulates into the flat buffer
@@ -340,8 +344,12 @@ def run_ours(args, rank, local_rank, world):
             if cfg4:  # a training step: the ADC statistics follow the gradients (parallel.view_sharded_step)
                 P.sync_adc(r)
         if e2e:
-            loss_ready.synchronize()
-            return float(loss_host[0])  # device -> host read of the step's result
+            if len(c2w_devs) == 1:
+                loss_ready.synchronize()
+                return float(loss_host[0])  # device -> host read of the step's result
+            # several views per step: read at the end of the step (letting the host run a whole multi-view eager
+            # step ahead makes the caching allocator grow instead of recycling: cfg 4 on one GPU 316 -> 187 it/s)
+            return float(total.item())
         return total
 
     def fwd_only():
@@ -391,7 +399,12 @@ def run_ours(args, rank, local_rank, world):
 
     # single-GPU, one view per step: the product's fast path is the CUDA-graph step (static duplicate capacity, no
     # host round trip, two graph launches per step); `--no-graph` times the eager step instead
-    ms_fwd = timed(fwd_only, args.steps)  # forward-only FPS: the eager render call (viewer / evaluation loop)
+    # forward-only FPS: the eager render call (viewer / evaluation loop), one 8-byte read-back of the duplicate count
+    # per frame.  (Measured: the same loop with the static capacity and NO per-frame synchronisation is slower, 637
+    # against 893 FPS -- the host runs frames ahead and the caching allocator grows instead of recycling.)
+    cap_saved, r.static_capacity = r.static_capacity, None
+    ms_fwd = timed(fwd_only, args.steps)
+    r.static_capacity = cap_saved
     gstep = None
     if world == 1 and not cfg4 and not args.no_graph:
         from gaussian_splatting_3d_b200.graph import GraphedStep
