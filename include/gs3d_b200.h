@@ -121,7 +121,9 @@ int gs3d_project_cull_fused(uint32_t N, const float *mean, const float *qvec,
  * ascending int64 sort of the reference's keys with ties (same tile, same depth bits) in
  * ascending Gaussian id -- one of the orders the reference's atomic emission can produce.
  * gaussian_ids int32 [n_dub], start/end int32 [n_tiles] (-1 = empty), sorted_keys int64 [n_dub]
- * optional (NULL to skip).  Returns GS3D_ECOUNT (after a sync) only when check_count != 0 and the
+ * optional (NULL to skip).  Limits: N, n_dub < 2^30; n_tiles_h, n_tiles_w <= 65535 and n_tiles < 2^24 (the rects
+ * travel through the depth sort packed in 8 bytes; rects are expected clamped to the tile grid, as
+ * gs/culling.py:29-31 and gs3d_tile_culling_aabb_count produce them).  Returns GS3D_ECOUNT (after a sync) only when check_count != 0 and the
  * rects do not add up to n_dub. */
 size_t gs3d_binning_scratch_bytes(uint32_t N, uint32_t n_dub);
 int gs3d_tile_culling_aabb_start_end(uint32_t N, uint32_t n_dub, uint32_t n_tiles_h,
