@@ -557,8 +557,14 @@ __device__ __forceinline__ void emit_quad(const CompositeParams &p, size_t g, in
 // Early termination: every warp publishes "some pixel still alive" with its arrival; when no warp is alive the
 // producer arms the next stage as a sentinel (0 Gaussians) and the warps leave.
 
-constexpr int RS = 4;  // ring stages
-constexpr int RG = 8;  // Gaussians per stage
+#ifndef GS3D_RING_STAGES
+#define GS3D_RING_STAGES 4
+#endif
+#ifndef GS3D_RING_GAUSSIANS
+#define GS3D_RING_GAUSSIANS 8
+#endif
+constexpr int RS = GS3D_RING_STAGES;     // ring stages (power of two)
+constexpr int RG = GS3D_RING_GAUSSIANS;  // Gaussians per stage (<= 8: one mask byte per warp and stage)
 
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
