@@ -86,3 +86,28 @@ def test_schedulers_and_activations():
     assert abs(inv_activations["exp"](0.01) - np.log(0.01)) < 1e-12
     x = torch.tensor([0.2, 0.7])
     assert torch.allclose(activations["sigmoid"](inv_activations["sigmoid"](x)), x, atol=1e-6)
+
+
+def test_bench_weak_scaling_poses_are_centred_and_small():
+    """bench.views_for: one pose per rank, yawed `yaw_step` degrees apart around the cfg-2 pose; rank poses of the
+    default step stay inside the scene's 5 % margin (about +-3.8 degrees), world == 1 is the identity pose."""
+    import math
+    import sys
+    from pathlib import Path
+
+    import torch
+
+    sys.path.insert(0, str(Path(__file__).resolve().parent.parent))
+    import bench
+
+    assert torch.equal(bench.views_for(1, torch)[0], torch.eye(3, 4))
+    for world in (2, 4, 8):
+        views = bench.views_for(world, torch, 0.5)
+        assert len(views) == world
+        yaws = [math.degrees(math.atan2(float(v[0, 2]), float(v[0, 0]))) for v in views]
+        assert abs(sum(yaws)) < 1e-4 and max(abs(y) for y in yaws) <= 0.5 * (world - 1) / 2 + 1e-4 < 3.8
+        for a, b in zip(yaws[:-1], yaws[1:]):
+            assert abs((b - a) - 0.5) < 1e-4
+        for v in views:  # proper rotations, no translation
+            R = v[:, :3]
+            assert torch.allclose(R @ R.T, torch.eye(3), atol=1e-6) and float(v[:, 3].abs().max()) == 0.0
