@@ -11,6 +11,17 @@ if str(ROOT) not in sys.path:
 os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
 
 
+def free_port():
+    """A TCP port that is free right now on 127.0.0.1 (bind to 0, read it back): the multi-process tests used
+    pid-derived ports, some of them inside the kernel's ephemeral range (32768+), where a connection of an earlier
+    test could already sit -- one rendezvous in three failed with 'address already in use'."""
+    import socket
+
+    with socket.socket(socket.AF_INET, socket.SOCK_STREAM) as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
 

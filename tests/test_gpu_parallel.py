@@ -5,6 +5,8 @@ import os
 
 import pytest
 import torch
+
+from conftest import free_port
 import torch.distributed as dist
 import torch.multiprocessing as mp
 
@@ -98,7 +100,7 @@ def _worker(rank, world, port, q):
 def test_two_gpu_tile_sharded_render_and_view_sharded_training():
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
-    port = 29600 + (os.getpid() % 2000)
+    port = free_port()
     procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
     for p in procs:
         p.start()
@@ -157,7 +159,7 @@ def test_two_gpu_fused_gradient_exchange(use_multicast):
     NVSwitch multimem) + small all-reduce == serial sum over the four views."""
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
-    port = 29700 + (os.getpid() % 2000) + (7 if use_multicast else 0)
+    port = free_port()
     procs = [ctx.Process(target=_worker_fused, args=(r, 2, port, q, use_multicast)) for r in range(2)]
     for p in procs:
         p.start()
@@ -223,7 +225,7 @@ def test_two_gpu_sparse_gradient_exchange(mode):
     four views; the union covers every non-zero row."""
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
-    port = 29900 + (os.getpid() % 2000) + {"sparse": 0, "push": 11, "push-peer": 23, "pull": 37, "pull-peer": 41}[mode]
+    port = free_port()
     procs = [ctx.Process(target=_worker_sparse, args=(r, 2, port, q, mode)) for r in range(2)]
     for p in procs:
         p.start()
@@ -298,7 +300,7 @@ def test_two_gpu_view_sharded_training_across_adaptive_control():
     of N -- statistics after the density-control step equal the serial ones, stale buffers raise."""
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
-    port = 30100 + (os.getpid() % 2000)
+    port = free_port()
     procs = [ctx.Process(target=_worker_adc, args=(r, 2, port, q)) for r in range(2)]
     for p in procs:
         p.start()

@@ -3,6 +3,8 @@ flat-gradient all-reduce of view-sharded training over a world_size-2 gloo group
 import os
 
 import torch
+
+from conftest import free_port
 import torch.distributed as dist
 import torch.multiprocessing as mp
 
@@ -74,7 +76,9 @@ def _worker(rank, world, port, q):
         m.cnt += 1
     flat.all_reduce()
     P.sync_adc(m)
-    q.put((rank, views, flat.flat.clone(), m.grad_mean.clone(), m.cnt.clone(),
+    # (numpy arrays travel through the queue BY VALUE; torch tensors travel as shared-memory handles served by this
+    # process, and the parent's get() raced with this worker's exit: one run in eight failed with FileNotFoundError)
+    q.put((rank, views, flat.flat.clone().numpy(), m.grad_mean.clone().numpy(), m.cnt.clone().numpy(),
            [p.grad.data_ptr() == vw.data_ptr() for p, vw in zip(flat.params, flat.views)]))
     dist.barrier()
     dist.destroy_process_group()
@@ -83,7 +87,7 @@ def _worker(rank, world, port, q):
 def test_view_sharded_gradient_allreduce_gloo_world2():
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
-    port = 29500 + (os.getpid() % 2000)
+    port = free_port()
     procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
     for p in procs:
         p.start()
@@ -91,6 +95,7 @@ def test_view_sharded_gradient_allreduce_gloo_world2():
     for p in procs:
         p.join(timeout=60)
         assert p.exitcode == 0
+    res = [tuple(torch.from_numpy(x) if hasattr(x, "dtype") and not torch.is_tensor(x) else x for x in t) for t in res]
     (r0, v0, f0, gm0, c0, al0), (r1, v1, f1, gm1, c1, al1) = res
     assert v0 == [0, 2, 4, 6] and v1 == [1, 3, 5, 7]
     assert all(al0) and all(al1)  # .grad aliases the flat buffer
@@ -152,7 +157,7 @@ def _worker_adc_baseline(rank, world, port, q):
     m.cnt += 1
     P.sync_adc(m)
     out.append((m.grad_mean.clone(), m.cnt.clone()))
-    q.put((rank, out))
+    q.put((rank, [(gm.numpy(), c.numpy()) for gm, c in out]))  # by value (see _worker)
     dist.barrier()
     dist.destroy_process_group()
 
@@ -160,7 +165,7 @@ def _worker_adc_baseline(rank, world, port, q):
 def test_sync_adc_baseline_follows_buffer_resets_gloo_world2():
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
-    port = 31500 + (os.getpid() % 2000)
+    port = free_port()
     procs = [ctx.Process(target=_worker_adc_baseline, args=(r, 2, port, q)) for r in range(2)]
     for p in procs:
         p.start()
@@ -168,6 +173,7 @@ def test_sync_adc_baseline_follows_buffer_resets_gloo_world2():
     for p in procs:
         p.join(timeout=60)
         assert p.exitcode == 0
+    res = [(rk, [(torch.from_numpy(gm), torch.from_numpy(c)) for gm, c in out]) for rk, out in res]
     for (gm0, c0), (gm1, c1) in zip(res[0][1], res[1][1]):
         assert torch.equal(gm0, gm1) and torch.equal(c0, c1)
     o = res[0][1]
